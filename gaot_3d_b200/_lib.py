@@ -1,0 +1,85 @@
+"""ctypes binding of libgaot_b200.so -- the binding a maintainer of the reference would add
+(see INTEGRATION.md).  Declares every symbol of include/gaot_b200.h.  There is NO fallback:
+if the library is missing or a call fails, an exception is raised."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_int, c_int32, c_int64, c_uint64, c_double, c_size_t, c_void_p, c_char_p, POINTER
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgaot_b200.so")
+
+
+class GaotError(RuntimeError):
+    pass
+
+
+class MlpDesc(ctypes.Structure):
+    _fields_ = [("n_layers", c_int32), ("dims", c_int32 * 8)]
+
+
+P = c_void_p
+_SIGS = {
+    "gaot_last_error": (c_char_p, []),
+    "gaot_abi_version": (c_int, []),
+    "gaot_launch_count": (c_int64, []),
+    "gaot_launch_count_reset": (None, []),
+    "gaot_radius_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "gaot_radius_count": (c_int, [P, c_int64, P, c_int64, c_double, c_int, P, c_size_t, P, POINTER(c_int64), P]),
+    "gaot_radius_emit": (c_int, [P, c_int64, P, c_int64, c_double, c_int, P, c_size_t, P, P, P, P]),
+    "gaot_knn_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "gaot_knn": (c_int, [P, c_int64, P, c_int64, c_int, P, c_size_t, P, P, P]),
+    "gaot_coalesce_workspace_bytes": (c_size_t, [c_int64]),
+    "gaot_coalesce": (c_int, [P, P, c_int64, c_int64, c_int64, P, c_size_t, P, P, P, POINTER(c_int64), P]),
+    "gaot_edge_mask_workspace_bytes": (c_size_t, [c_int64]),
+    "gaot_edge_mask": (c_int, [P, P, c_int64, c_double, c_uint64, c_uint64, P, c_size_t, P, P, P, POINTER(c_int64), P]),
+    "gaot_csr_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "gaot_csr_from_edges": (c_int, [P, P, c_int64, c_int64, c_int64, c_int, P, c_size_t, P, P, P, P, P]),
+    "gaot_gno_workspace_bytes": (c_size_t, [c_int64, c_int64, POINTER(MlpDesc)]),
+    "gaot_gno_forward": (c_int, [P, c_int64, P, c_int64, P, c_int32, P, P, P, c_int64, POINTER(MlpDesc), P,
+                                 c_int, c_int, c_int, P, c_size_t, P, P]),
+    "gaot_gno_backward": (c_int, [P, c_int64, P, c_int64, P, c_int32, P, P, P, c_int64, POINTER(MlpDesc), P,
+                                  c_int, c_int, c_int, P, P, c_size_t, P, P, P]),
+    "gaot_geo_stats": (c_int, [P, c_int64, P, c_int64, P, P, P, P]),
+    "gaot_geo_zscore_workspace_bytes": (c_size_t, [c_int64]),
+    "gaot_geo_zscore": (c_int, [P, c_int64, c_int32, P, c_size_t, P]),
+    "gaot_attn_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32, c_int32, c_int32]),
+    "gaot_attn_forward": (c_int, [P, P, P, c_int64, c_int64, c_int32, c_int32, c_int32, P, P, c_size_t, P, P, P]),
+    "gaot_attn_backward": (c_int, [P, P, P, P, P, P, c_int64, c_int64, c_int32, c_int32, c_int32, P,
+                                   P, c_size_t, P, P, P, P]),
+    "gaot_radius_host": (c_int, [P, c_int64, P, c_int64, c_double, c_int, P, P, POINTER(c_int64)]),
+    "gaot_knn_host": (c_int, [P, c_int64, P, c_int64, c_int, P, P, POINTER(c_int64)]),
+    "gaot_tc_probe": (c_int, [P, P, P, c_int, c_int, c_int, P]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGS)
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GaotError(
+            f"{LIB_PATH} not found: build it with `python -m gaot_3d_b200.build` "
+            "(there is no CPU / PyTorch fallback for the B200 hot path)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)           # AttributeError if the ABI and the header disagree
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().gaot_last_error()
+        msg = msg.decode() if msg else ""
+        if rc == 4:
+            raise NotImplementedError(f"{what}: {msg}")
+        if rc == 1:
+            raise ValueError(f"{what}: {msg}")
+        raise GaotError(f"{what} failed (status {rc}): {msg}")

@@ -1,0 +1,126 @@
+// tc05.cuh -- thin inline-PTX layer over Blackwell tcgen05 / TMEM / mbarrier (sm_100a).
+//
+// Shared-memory operand format used by every tensor-core kernel in this library
+// ("chunk-major", no swizzle): a bf16 tile of R rows x C columns is stored as
+//     offset(r, c) = (c / 8) * (R * 16) + r * 16 + (c % 8) * 2          [bytes]
+// i.e. 16-byte chunks (8 elements along the column axis); all rows of one chunk are contiguous.
+// Each 8-row x 16-byte block is one 128-byte tcgen05 "core matrix".  The same tile serves as
+//   * a K-major operand   (rows = M/N index, columns = K):  LBO = R*16 (next K chunk), SBO = 128
+//   * an MN-major operand (rows = K index, columns = M/N):  LBO = 128 (next 8 K rows), SBO = R*16
+// (canonical INTERLEAVE layouts of cute::UMMA::make_umma_desc, mma_sm100_desc.hpp), so that
+// e.g. V[keys,d] feeds P*V and dS^T[keys,q] feeds both dK and dQ without any transposed copy.
+#pragma once
+#include <cstdint>
+#include <cuda_bf16.h>
+
+namespace gaot { namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- shared-memory matrix descriptor (SWIZZLE_NONE, version 1 = Blackwell) ----
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// K-major operand over a chunk-major tile with `rows` rows; kstep = index of the 16-element K slice
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_saddr, uint32_t rows, uint32_t kstep) {
+    return make_desc(tile_saddr + kstep * 2u * rows * 16u, rows * 16u, 128u);
+}
+// MN-major operand over a chunk-major tile with `rows` (= K extent) rows
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_saddr, uint32_t rows, uint32_t kstep) {
+    return make_desc(tile_saddr + kstep * 256u, 128u, rows * 16u);
+}
+
+// ---- instruction descriptor: kind::f16, BF16 x BF16 -> FP32 ----
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+// arrives on the mbarrier when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void mma_commit(uint64_t* mbar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(mbar)) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+// make generic-proxy shared-memory writes visible to the async proxy (tensor core operand reads)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// ---- TMEM allocation (one full warp executes these) ----
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// ---- TMEM -> registers: 32 lanes x 32 consecutive fp32 columns (thread t <-> lane base+t) ----
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- mbarrier ----
+__device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* mbar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t}\n" : "=r"(ok) : "r"(smem_u32(mbar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded spin: a tensor-core pipeline that never signals is a bug; trap instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
+    for (uint32_t spins = 0; !mbar_try_wait(mbar, parity); ++spins)
+        if (spins > (1u << 24)) __trap();
+}
+
+// ---- packing helpers ----
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+// byte offset of element (r, c) in a chunk-major bf16 tile with `rows` rows
+__device__ __forceinline__ uint32_t cm_off(uint32_t rows, uint32_t r, uint32_t c) {
+    return (c >> 3) * (rows * 16u) + r * 16u + (c & 7u) * 2u;
+}
+
+}}  // namespace gaot::tc

@@ -1,0 +1,175 @@
+"""Online bipartite graph build between physical points and latent tokens.
+
+Drop-in for reference src/model/layers/magno.py:72-371 (`parse_neighbor_strategy`,
+`get_neighbor_strategy`, `apply_neighbor_sampling`): same signatures, same edge_index
+conventions (row 0 = source index, row 1 = query index, int64, global batched indices), same
+error behaviour (ValueError on an unknown strategy, empty [2,0] tensor when nothing matches).
+Underneath: the cell-list radius / kNN kernels and the radix-sort coalesce of libgaot_b200.so.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple, Union
+
+import torch
+
+from . import ops
+
+PYG_MAX_NUM_NEIGHBORS = 32   # torch_geometric.nn.radius default, never overridden by the reference
+
+
+def parse_neighbor_strategy(neighbor_strategy: Union[str, List[str]]) -> Tuple[str, str]:
+    if isinstance(neighbor_strategy, str):
+        return neighbor_strategy, neighbor_strategy
+    if isinstance(neighbor_strategy, (list, tuple)) and len(neighbor_strategy) == 2:
+        return neighbor_strategy[0], neighbor_strategy[1]
+    raise ValueError(f"neighbor_strategy must be str or list of length 2, got {neighbor_strategy}")
+
+
+def parse_geoembed_strategy(use_geoembed: Union[bool, List[bool]]) -> Tuple[bool, bool]:
+    if isinstance(use_geoembed, bool):
+        return use_geoembed, use_geoembed
+    if isinstance(use_geoembed, (list, tuple)) and len(use_geoembed) == 2:
+        return bool(use_geoembed[0]), bool(use_geoembed[1])
+    raise ValueError(f"use_geoembed must be bool or list of length 2, got {use_geoembed}")
+
+
+def _example_slices(batch: Optional[torch.Tensor], n: int, num_examples: int):
+    """[(start, end)] per example from a sorted batch vector (PyG ptr semantics)."""
+    if batch is None or num_examples == 1:
+        return [(0, n)]
+    ptr = torch.searchsorted(batch.contiguous(), torch.arange(num_examples + 1, device=batch.device, dtype=batch.dtype))
+    ptr = ptr.tolist()
+    return [(ptr[i], ptr[i + 1]) for i in range(num_examples)]
+
+
+def _num_examples(*batches) -> int:
+    b = 1
+    for bt in batches:
+        if bt is not None and bt.numel():
+            b = max(b, int(bt[-1].item()) + 1)      # sorted ascending
+    return b
+
+
+def _per_example(fn, x, y, batch_x, batch_y):
+    """Run a single-example search per batch element; indices are offset back to global."""
+    B = _num_examples(batch_x, batch_y)
+    if B == 1:
+        return fn(x, y)
+    sx, sy = _example_slices(batch_x, x.shape[0], B), _example_slices(batch_y, y.shape[0], B)
+    rows, cols = [], []
+    for (x0, x1), (y0, y1) in zip(sx, sy):
+        r, c = fn(x[x0:x1], y[y0:y1])
+        rows.append(r + y0)
+        cols.append(c + x0)
+    return torch.cat(rows), torch.cat(cols)
+
+
+def radius_graph(x, y, r, batch_x=None, batch_y=None, max_num_neighbors: int = PYG_MAX_NUM_NEIGHBORS):
+    """torch_geometric.nn.radius(x, y, r, batch_x, batch_y): returns [2,E], row 0 = y index, row 1 = x index."""
+    ry, cx = _per_example(lambda a, b: ops.radius(a, b, r, max_num_neighbors), x, y, batch_x, batch_y)
+    return torch.stack([ry, cx])
+
+
+def knn_graph(x, y, k, batch_x=None, batch_y=None):
+    """torch_geometric.nn.knn(x, y, k, batch_x, batch_y): returns [2, ny*k], row 0 = y index, row 1 = x index."""
+    ry, cx = _per_example(lambda a, b: ops.knn(a, b, k), x, y, batch_x, batch_y)
+    return torch.stack([ry, cx])
+
+
+def _tag(ei: torch.Tensor, query_sorted: bool) -> torch.Tensor:
+    ei._gaot_query_sorted = query_sorted     # side-band hint: CSR build can skip its sort
+    return ei
+
+
+def _coalesced(parts, n0: int, n1: int) -> torch.Tensor:
+    cat = torch.cat(parts, dim=1)
+    r0, r1 = ops.coalesce(cat[0], cat[1], max(n0 - 1, 0), max(n1 - 1, 0))
+    return torch.stack([r0, r1])
+
+
+def _encoder_edges(strategy, phys_pos, batch_phys, latent_pos, batch_latent, radius, k):
+    n_phys, n_lat = phys_pos.shape[0], latent_pos.shape[0]
+    if strategy == "knn":          # each physical point -> its k nearest latent tokens: [phys, latent]
+        return _tag(knn_graph(latent_pos, phys_pos, k, batch_latent, batch_phys), False)
+    if strategy == "radius":       # latent tokens as centres: raw [latent, phys] -> flip
+        return _tag(radius_graph(phys_pos, latent_pos, radius, batch_phys, batch_latent).flip(0).contiguous(), True)
+    if strategy == "bidirectional":
+        e_knn = knn_graph(latent_pos, phys_pos, k, batch_latent, batch_phys)
+        e_rad = radius_graph(phys_pos, latent_pos, radius, batch_phys, batch_latent).flip(0)
+        return _tag(_coalesced([e_knn, e_rad], n_phys, n_lat), False)
+    raise ValueError(f"Unknown encoder strategy: {strategy}")
+
+
+def _decoder_edges(strategy, phys_pos, batch_phys, latent_pos, batch_latent, radius, k):
+    n_phys, n_lat = phys_pos.shape[0], latent_pos.shape[0]
+    if strategy == "reverse":      # flip of the *bidirectional* encoder graph, whatever the encoder uses
+        enc = _encoder_edges("bidirectional", phys_pos, batch_phys, latent_pos, batch_latent, radius, k)
+        return _tag(enc.flip(0).contiguous(), True)
+    if strategy == "knn":
+        return _tag(knn_graph(latent_pos, phys_pos, k, batch_latent, batch_phys).flip(0).contiguous(), True)
+    if strategy == "radius":
+        return _tag(radius_graph(latent_pos, phys_pos, radius, batch_latent, batch_phys).flip(0).contiguous(), True)
+    if strategy == "bidirectional":
+        e_knn = knn_graph(latent_pos, phys_pos, k, batch_latent, batch_phys).flip(0)
+        e_rad = radius_graph(latent_pos, phys_pos, radius, batch_latent, batch_phys).flip(0)
+        return _tag(_coalesced([e_knn, e_rad], n_lat, n_phys), False)
+    raise ValueError(f"Unknown decoder strategy: {strategy}")
+
+
+def get_neighbor_strategy(neighbor_strategy: str, phys_pos: torch.Tensor, batch_idx_phys: torch.Tensor,
+                          latent_tokens_pos: torch.Tensor, batch_idx_latent: torch.Tensor, radius: float,
+                          k_neighbors: int = 1, is_decoder: bool = False) -> torch.Tensor:
+    """Same contract as reference magno.py:116-163.  Encoder output is [phys_idx; latent_idx],
+    decoder output [latent_idx; phys_idx].  CUDA tensors only (no CPU fallback by design: the
+    reference's CPU callers -- collate_functions.py:97, stat.py:182 -- become unnecessary)."""
+    if not phys_pos.is_cuda:
+        raise RuntimeError("gaot_3d_b200.get_neighbor_strategy builds graphs on the GPU only; move the positions "
+                           "to a CUDA device (set asynchronous_graph_building=False, precompute_edges=False)")
+    fn = _decoder_edges if is_decoder else _encoder_edges
+    return fn(neighbor_strategy, phys_pos, batch_idx_phys, latent_tokens_pos, batch_idx_latent,
+              float(radius), int(k_neighbors))
+
+
+_mask_calls = [0]
+
+
+def apply_neighbor_sampling(edge_index: torch.Tensor, num_query_nodes: int, device=None,
+                            sampling_strategy: Optional[str] = None, max_neighbors: Optional[int] = None,
+                            sample_ratio: Optional[float] = None, training: bool = True) -> torch.Tensor:
+    """Reference magno.py:297-371.  None -> passthrough; 'ratio' -> Philox edge mask kernel (training
+    only); 'max_neighbors' -> random <= K edges per over-full query (kept in torch, rarely used)."""
+    if sampling_strategy is None:
+        return edge_index
+    E = edge_index.shape[1]
+    if num_query_nodes == 0 or E == 0:
+        return edge_index
+    if sampling_strategy == "ratio":
+        if sample_ratio is None:
+            raise ValueError("sample_ratio must be provided when using 'ratio' sampling strategy")
+        if sample_ratio >= 1.0 or not training:
+            return edge_index
+        seed = int(torch.initial_seed())
+        _mask_calls[0] += 1
+        r0, r1 = ops.edge_mask(edge_index[0], edge_index[1], 1.0 - float(sample_ratio), seed,
+                               offset=_mask_calls[0] * ((E + 3) // 4))
+        out = torch.stack([r0, r1])
+        out._gaot_query_sorted = bool(getattr(edge_index, "_gaot_query_sorted", False))
+        return out
+    if sampling_strategy == "max_neighbors":
+        if max_neighbors is None:
+            raise ValueError("max_neighbors must be provided when using 'max_neighbors' sampling strategy")
+        dest = edge_index[1]
+        counts = torch.bincount(dest, minlength=num_query_nodes)
+        if not bool((counts > max_neighbors).any()):
+            return edge_index
+        # random rank inside each query segment; keep ranks < max_neighbors (one vectorised pass
+        # instead of the reference's Python loop over over-full queries)
+        key = torch.rand(E, device=edge_index.device)
+        order = torch.argsort(dest.to(torch.float64) + key.to(torch.float64) * 0.5, stable=True)
+        sorted_dest = dest[order]
+        start = torch.cumsum(counts, 0) - counts
+        rank = torch.arange(E, device=edge_index.device) - start[sorted_dest]
+        keep = torch.zeros(E, dtype=torch.bool, device=edge_index.device)
+        keep[order[rank < max_neighbors]] = True
+        return edge_index[:, keep]
+    raise ValueError(f"Invalid sampling strategy: {sampling_strategy}")

@@ -1,0 +1,203 @@
+"""Latent-token transformer -- drop-in for reference src/model/layers/attn.py.
+
+Config dataclasses keep the reference's field names/defaults; modules keep parameter names
+(`attn.{q,k,v,o}_proj.weight`, `attn.rotary_emb.freqs`, `ffn.{w1,w2,w3}.weight`,
+`attn_norm.weight`, `ffn_norm.weight`, `skip_proj.*`).  The attention core (RoPE + softmax(QK^T)V,
+reference :110-128) is the tcgen05/TMEM flash kernel of this package; projections, SwiGLU FFN
+and RMSNorm stay torch/cuBLAS.
+"""
+from dataclasses import dataclass, field, fields, is_dataclass
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+
+
+@dataclass
+class AttentionConfig:
+    hidden_size: int = 256
+    num_heads: int = 8
+    num_kv_heads: int = 8
+    use_conditional_norm: bool = False
+    cond_norm_hidden_size: int = 4
+    atten_dropout: float = 0.1
+    positional_embedding: str = "absolute"
+    H: Optional[int] = None
+    W: Optional[int] = None
+
+
+@dataclass
+class FFNConfig:
+    hidden_size: int = 1024
+    use_conditional_norm: bool = False
+    cond_norm_hidden_size: int = 4
+
+
+@dataclass
+class TransformerConfig:
+    patch_size: int = 8
+    hidden_size: int = 256
+    use_attn_norm: bool = True
+    use_ffn_norm: bool = True
+    norm_eps: float = 1e-6
+    num_layers: int = 3
+    positional_embedding: str = "absolute"
+    use_long_range_skip: bool = True
+    attn_config: AttentionConfig = field(default_factory=AttentionConfig)
+    ffn_config: FFNConfig = field(default_factory=FFNConfig)
+
+
+def _cfg_dict(obj) -> dict:
+    if is_dataclass(obj):
+        return {f.name: getattr(obj, f.name) for f in fields(obj)}
+    return dict(obj)
+
+
+class RotaryEmbedding(nn.Module):
+    """Carrier of the `freqs` state_dict entry of rotary_embedding_torch.RotaryEmbedding(dim)
+    (theta 10000, non-trainable nn.Parameter); the rotation itself is fused into the attention
+    kernels' Q/K load."""
+
+    def __init__(self, dim, theta=10000.0):
+        super().__init__()
+        self.freqs = nn.Parameter(1.0 / (theta ** (torch.arange(0, dim, 2)[: dim // 2].float() / dim)), requires_grad=False)
+
+
+class GroupQueryFlashAttention(nn.Module):
+    def __init__(self, input_size: int, output_size: int, hidden_size: int = 128, num_heads: int = 8,
+                 num_kv_heads: int = 4, use_conditional_norm: bool = False, cond_norm_hidden_size: int = 4,
+                 atten_dropout: float = 0.0, H: int = 64, W: int = 64, positional_embedding: str = "absolute"):
+        super().__init__()
+        assert hidden_size % num_heads == 0, f"hidden_size {hidden_size} must be divisible by num_heads {num_heads}"
+        assert num_heads % num_kv_heads == 0, f"num_heads {num_heads} must be divisible by num_kv_heads {num_kv_heads}"
+        self.num_heads, self.num_kv_heads = num_heads, num_kv_heads
+        self.num_repeat = num_heads // num_kv_heads
+        self.head_dim = hidden_size // num_heads
+        self.atten_dropout = atten_dropout
+        kv = self.head_dim * num_kv_heads
+        self.q_proj = nn.Linear(input_size, hidden_size, bias=False)
+        self.k_proj = nn.Linear(input_size, kv, bias=False)
+        self.v_proj = nn.Linear(input_size, kv, bias=False)
+        self.o_proj = nn.Linear(hidden_size, output_size, bias=False)
+        if use_conditional_norm:
+            raise NotImplementedError("time-conditional norm is unused by the 3-D static path (default_set.py:59)")
+        self.correction = None
+        if positional_embedding == "rope":
+            self.rotary_emb = RotaryEmbedding(dim=self.head_dim)
+
+    def forward(self, x, condition: Optional[float] = None, relative_positions: Optional[torch.Tensor] = None):
+        lead = x.shape[:-2]
+        x3 = x.reshape(-1, x.shape[-2], x.shape[-1])
+        q, k, v = self.q_proj(x3), self.k_proj(x3), self.v_proj(x3)
+        if self.training and self.atten_dropout > 0.0:
+            # reference attn.py:122-126 applies dropout inside SDPA; the Philox dropout path of the
+            # tcgen05 kernel is not built yet -> fail loudly rather than silently change semantics
+            raise NotImplementedError("attention dropout > 0 in training mode is not supported yet: set "
+                                      "attn_config.atten_dropout=0.0 (or call .eval())")
+        freqs = self.rotary_emb.freqs if relative_positions is not None else None
+        o = ops.attention(q, k, v, self.num_heads, self.num_kv_heads, rope_freqs=freqs)
+        return self.o_proj(o.to(x.dtype)).reshape(*lead, x.shape[-2], -1)
+
+    @classmethod
+    def from_config(cls, input_size: int, output_size: int, config: AttentionConfig):
+        kw = _cfg_dict(config)
+        for extra in ("D",):
+            kw.pop(extra, None)
+        return cls(input_size, output_size, **kw)
+
+
+class FFN(nn.Module):
+    def __init__(self, input_size: int, output_size: int, hidden_size: int = 256, use_conditional_norm: bool = False,
+                 cond_norm_hidden_size: int = 4):
+        super().__init__()
+        self.w1 = nn.Linear(input_size, hidden_size, bias=False)
+        self.w2 = nn.Linear(hidden_size, output_size, bias=False)
+        self.w3 = nn.Linear(input_size, hidden_size, bias=False)
+        if use_conditional_norm:
+            raise NotImplementedError("time-conditional norm is unused by the 3-D static path")
+        self.correction = None
+
+    def forward(self, x, condition: Optional[float] = None):
+        return self.w2(F.silu(self.w1(x)) * self.w3(x))
+
+    @classmethod
+    def from_config(cls, input_size: int, output_size: int, config: FFNConfig):
+        return cls(input_size, output_size, **_cfg_dict(config))
+
+
+class RMSNorm(nn.Module):
+    def __init__(self, dim: int, eps: float = 1e-6):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(dim))
+
+    def forward(self, x):
+        xf = x.float()
+        return (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + self.eps)).type_as(x) * self.weight
+
+
+class TransformerBlock(nn.Module):
+    def __init__(self, input_size: int, output_size: int, use_attn_norm: bool = True, use_ffn_norm: bool = True,
+                 norm_eps: float = 1e-6, attn_config: AttentionConfig = None, ffn_config: FFNConfig = None,
+                 skip_connection: bool = False):
+        super().__init__()
+        attn_config = attn_config or AttentionConfig()
+        ffn_config = ffn_config or FFNConfig()
+        self.attn = GroupQueryFlashAttention.from_config(input_size, attn_config.hidden_size, config=attn_config)
+        self.ffn = FFN.from_config(attn_config.hidden_size, output_size, config=ffn_config)
+        self.attn_norm = RMSNorm(input_size, eps=norm_eps) if use_attn_norm else None
+        self.ffn_norm = RMSNorm(attn_config.hidden_size, eps=norm_eps) if use_ffn_norm else None
+        self.skip_connection = skip_connection
+        if skip_connection:
+            self.skip_proj = nn.Linear(input_size + output_size, input_size)
+
+    def forward(self, x, condition=None, relative_positions=None, skip=None):
+        if self.skip_connection and skip is not None:
+            x = self.skip_proj(torch.cat([x, skip], dim=-1))
+        h = x if self.attn_norm is None else self.attn_norm(x)
+        h = x + self.attn(h, condition=condition, relative_positions=relative_positions)
+        h = h if self.ffn_norm is None else self.ffn_norm(h)      # reference quirk: residual taken after the norm
+        return h + self.ffn(h, condition=condition)
+
+    @classmethod
+    def from_config(cls, input_size: int, output_size: int, skip_connection: bool = False,
+                    config: TransformerConfig = None):
+        config = config or TransformerConfig()
+        config.attn_config.positional_embedding = config.positional_embedding
+        kw = _cfg_dict(config)
+        for k in ("num_layers", "hidden_size", "positional_embedding", "use_long_range_skip", "patch_size"):
+            kw.pop(k)
+        return cls(input_size, output_size, skip_connection=skip_connection, **kw)
+
+
+class Transformer(nn.Module):
+    """U-ViT style stack: num_layers//2 encoder blocks, optional middle, num_layers//2 decoder
+    blocks consuming the encoder outputs LIFO through `skip_proj` (reference attn.py:246-325)."""
+
+    def __init__(self, input_size: int, output_size: int, config: TransformerConfig = None):
+        super().__init__()
+        config = config or TransformerConfig()
+        hs, nl = config.hidden_size, config.num_layers
+        self.use_long_range_skip = config.use_long_range_skip
+        self.input_proj = nn.Linear(input_size, hs) if input_size != hs else nn.Identity()
+        self.output_proj = nn.Linear(hs, output_size) if hs != output_size else nn.Identity()
+        mk = lambda skip: TransformerBlock.from_config(input_size=hs, output_size=hs, skip_connection=skip, config=config)
+        self.encoder_layers = nn.ModuleList(mk(False) for _ in range(nl // 2))
+        self.middle_layer = mk(False) if nl % 2 == 1 else None
+        self.decoder_layers = nn.ModuleList(mk(True) for _ in range(nl // 2))
+
+    def forward(self, x, condition=None, relative_positions=None):
+        x = self.input_proj(x)
+        skips = []
+        for layer in self.encoder_layers:
+            x = layer(x, condition=condition, relative_positions=relative_positions)
+            skips.append(x)
+        if self.middle_layer is not None:
+            x = self.middle_layer(x, condition=condition, relative_positions=relative_positions)
+        for layer in self.decoder_layers:
+            skip = skips.pop() if self.use_long_range_skip else None
+            x = layer(x, condition=condition, relative_positions=relative_positions, skip=skip)
+        return self.output_proj(x)

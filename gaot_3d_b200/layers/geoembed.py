@@ -1,0 +1,47 @@
+"""Geometric embedding -- drop-in for reference src/model/layers/geoembed.py ('statistical' method).
+
+Parameter names match (`mlp.0`, `mlp.2`).  The per-query statistics (count, mean/var of distance,
+centroid offset, covariance eigenvalues) and the global z-score are CUDA kernels (geo.cu); the
+9->64->out MLP on [N_q, 9] stays a torch GEMM.
+"""
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+
+class GeometricEmbedding(nn.Module):
+    def __init__(self, input_dim, output_dim, method="statistical", pooling="max", **kwargs):
+        super().__init__()
+        self.input_dim, self.output_dim = input_dim, output_dim
+        self.method, self.pooling, self.kwargs = method.lower(), pooling.lower(), kwargs
+        if self.pooling not in ("max", "mean"):
+            raise ValueError(f"Unsupported pooling method: {self.pooling}. Supported methods: 'max', 'mean'.")
+        if self.method == "statistical":
+            self.mlp = nn.Sequential(nn.Linear(self._get_stat_feature_dim(), 64), nn.ReLU(), nn.Linear(64, output_dim))
+        elif self.method == "pointnet":
+            # SURVEY.md §8(f) rank 3
+            raise NotImplementedError("'pointnet' geometric embedding is not built yet (statistical only)")
+        else:
+            raise ValueError(f"Unknown method: {self.method}")
+
+    def _get_stat_feature_dim(self):
+        return 3 + 2 * self.input_dim
+
+    def statistical_features(self, source_pos, query_pos, edge_index, normalize=True):
+        csr = ops.csr_of(edge_index, source_pos.shape[0], query_pos.shape[0])
+        feat = ops.geo_stats(source_pos, query_pos, csr, normalize=normalize)
+        if self.input_dim == 2:        # [N, Davg, Dvar, dx, dy, (dz), l0, l1, (l2)] -> drop the padded axis
+            feat = feat[:, [0, 1, 2, 3, 4, 6, 7]]
+        return feat
+
+    def forward(self, source_pos: torch.Tensor, query_pos: torch.Tensor, edge_index: torch.Tensor,
+                batch_source: Optional[torch.Tensor] = None, batch_query: Optional[torch.Tensor] = None,
+                neighbors_counts: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if neighbors_counts is not None:
+            raise NotImplementedError("neighbors_counts override is unused by the reference (magno.py:513-516)")
+        if self.input_dim == 2:
+            raise NotImplementedError("2-D statistical embedding needs the z-score on the reduced feature set")
+        return self.mlp(self.statistical_features(source_pos, query_pos, edge_index))

@@ -1,0 +1,363 @@
+"""Tensor-level host API over the C ABI (include/gaot_b200.h).
+
+PyTorch is plumbing only: device memory (torch.empty), the current CUDA stream and autograd
+bookkeeping.  Every function here launches hand-written sm_100a kernels from
+libgaot_b200.so through ctypes; CPU tensors are rejected (there is no fallback path).
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import MlpDesc, check
+
+_PRECISION = {"gno": 0}     # 0 = fp32 CUDA cores, 1 = bf16 tcgen05
+
+
+def set_gno_precision(name: str) -> None:
+    if name not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    _PRECISION["gno"] = 0 if name == "fp32" else 1
+
+
+def get_gno_precision() -> str:
+    return "fp32" if _PRECISION["gno"] == 0 else "bf16"
+
+
+def _lib_():
+    return _lib.load()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("gaot_3d_b200: the B200 hot path has no CPU fallback; got a CPU tensor "
+                               "(build graphs / run the model on a CUDA device)")
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(dev) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _ws(nbytes: int, dev) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
+
+
+def _pos3(p: torch.Tensor) -> torch.Tensor:
+    """float32 contiguous [n,3]; 2-D inputs are zero padded (dz*dz = 0 keeps distances exact)."""
+    if p.dim() != 2 or p.shape[1] not in (2, 3):
+        raise ValueError("positions must be [N, 2] or [N, 3]")
+    p = p.detach().to(torch.float32)
+    if p.shape[1] == 2:
+        p = torch.cat([p, p.new_zeros(p.shape[0], 1)], dim=1)
+    return p.contiguous()
+
+
+# ----------------------------------------------------------------------------- graph build
+def radius(x: torch.Tensor, y: torch.Tensor, r: float, max_num_neighbors: int = 32):
+    """For each y all x within r (strict), first `max_num_neighbors` by ascending x index.
+    Returns (row_y, col_x) int64, grouped by ascending y -- torch_cluster.radius semantics
+    (reference magno.py:193-200, :253-260)."""
+    _need_cuda(x, y)
+    x, y = _pos3(x), _pos3(y)
+    nx, ny, dev = x.shape[0], y.shape[0], x.device
+    lib = _lib_()
+    empty = torch.empty(0, dtype=torch.long, device=dev)
+    if nx == 0 or ny == 0:
+        return empty, empty.clone()
+    wsb = lib.gaot_radius_workspace_bytes(nx, ny)
+    ws = _ws(wsb, dev)
+    rowptr = torch.empty(ny + 1, dtype=torch.int32, device=dev)
+    E = ctypes.c_int64(0)
+    with torch.cuda.device(dev):
+        check(lib.gaot_radius_count(_p(x), nx, _p(y), ny, float(r), int(max_num_neighbors), _p(ws), wsb,
+                                    _p(rowptr), ctypes.byref(E), _stream(dev)), "radius_count")
+        out_y = torch.empty(E.value, dtype=torch.long, device=dev)
+        out_x = torch.empty(E.value, dtype=torch.long, device=dev)
+        if E.value:
+            check(lib.gaot_radius_emit(_p(x), nx, _p(y), ny, float(r), int(max_num_neighbors), _p(ws), wsb,
+                                       _p(rowptr), _p(out_y), _p(out_x), _stream(dev)), "radius_emit")
+    return out_y, out_x
+
+
+def knn(x: torch.Tensor, y: torch.Tensor, k: int):
+    """For each y its k nearest x, ascending (distance, index).  Returns (row_y, col_x) int64 of
+    length ny*min(k, nx), grouped by y -- torch_cluster.knn semantics (magno.py:183-189, :242-248)."""
+    _need_cuda(x, y)
+    x, y = _pos3(x), _pos3(y)
+    nx, ny, dev = x.shape[0], y.shape[0], x.device
+    lib = _lib_()
+    if nx == 0 or ny == 0:
+        e = torch.empty(0, dtype=torch.long, device=dev)
+        return e, e.clone()
+    k = min(int(k), nx)
+    wsb = lib.gaot_knn_workspace_bytes(nx, ny)
+    ws = _ws(wsb, dev)
+    out_y = torch.empty(ny * k, dtype=torch.long, device=dev)
+    out_x = torch.empty(ny * k, dtype=torch.long, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.gaot_knn(_p(x), nx, _p(y), ny, k, _p(ws), wsb, _p(out_y), _p(out_x), _stream(dev)), "knn")
+    return out_y, out_x
+
+
+def coalesce(row0: torch.Tensor, row1: torch.Tensor, max_row0: int, max_row1: int):
+    """Lexicographic sort + unique of an edge list (torch_geometric.utils.coalesce, magno.py:220,:293)."""
+    _need_cuda(row0, row1)
+    row0, row1 = row0.contiguous(), row1.contiguous()
+    E, dev = row0.numel(), row0.device
+    lib = _lib_()
+    if E == 0:
+        return row0.clone(), row1.clone()
+    wsb = lib.gaot_coalesce_workspace_bytes(E)
+    ws = _ws(wsb, dev)
+    o0, o1 = torch.empty_like(row0), torch.empty_like(row1)
+    e_dev = torch.empty(1, dtype=torch.long, device=dev)
+    e_host = ctypes.c_int64(0)
+    with torch.cuda.device(dev):
+        check(lib.gaot_coalesce(_p(row0), _p(row1), E, int(max_row0), int(max_row1), _p(ws), wsb, _p(o0), _p(o1),
+                                _p(e_dev), ctypes.byref(e_host), _stream(dev)), "coalesce")
+    return o0[: e_host.value], o1[: e_host.value]
+
+
+def edge_mask(row0: torch.Tensor, row1: torch.Tensor, p_drop: float, seed: int, offset: int = 0):
+    """Philox edge dropout + order-preserving compaction (torch_geometric dropout_edge, magno.py:367)."""
+    _need_cuda(row0, row1)
+    row0, row1 = row0.contiguous(), row1.contiguous()
+    E, dev = row0.numel(), row0.device
+    lib = _lib_()
+    if E == 0:
+        return row0.clone(), row1.clone()
+    wsb = lib.gaot_edge_mask_workspace_bytes(E)
+    ws = _ws(wsb, dev)
+    o0, o1 = torch.empty_like(row0), torch.empty_like(row1)
+    e_dev = torch.empty(1, dtype=torch.long, device=dev)
+    e_host = ctypes.c_int64(0)
+    with torch.cuda.device(dev):
+        check(lib.gaot_edge_mask(_p(row0), _p(row1), E, float(p_drop), int(seed) & (2 ** 64 - 1), int(offset),
+                                 _p(ws), wsb, _p(o0), _p(o1), _p(e_dev), ctypes.byref(e_host), _stream(dev)),
+              "edge_mask")
+    return o0[: e_host.value], o1[: e_host.value]
+
+
+@dataclass
+class Csr:
+    """Query-major CSR side-band of an edge list (int32)."""
+    rowptr: torch.Tensor    # [nq + 1]
+    src: torch.Tensor       # [E] source index per CSR slot
+    qry: torch.Tensor       # [E] query index per CSR slot
+    perm: torch.Tensor      # [E] original edge id per CSR slot
+    n_src: int
+    nq: int
+
+    @property
+    def E(self) -> int:
+        return int(self.src.numel())
+
+
+def build_csr(src: torch.Tensor, qry: torch.Tensor, n_src: int, nq: int, query_sorted: bool = False) -> Csr:
+    _need_cuda(src, qry)
+    src = src.to(torch.long).contiguous()
+    qry = qry.to(torch.long).contiguous()
+    E, dev = src.numel(), src.device
+    lib = _lib_()
+    rowptr = torch.empty(nq + 1, dtype=torch.int32, device=dev)
+    cs = torch.empty(E, dtype=torch.int32, device=dev)
+    cq = torch.empty(E, dtype=torch.int32, device=dev)
+    pm = torch.empty(E, dtype=torch.int32, device=dev)
+    wsb = lib.gaot_csr_workspace_bytes(E, nq)
+    ws = _ws(wsb, dev)
+    with torch.cuda.device(dev):
+        check(lib.gaot_csr_from_edges(_p(src), _p(qry), E, int(n_src), int(nq), 1 if query_sorted else 0,
+                                      _p(ws), wsb, _p(rowptr), _p(cs), _p(cq), _p(pm), _stream(dev)), "csr_from_edges")
+    return Csr(rowptr, cs, cq, pm, int(n_src), int(nq))
+
+
+def csr_of(edge_index: torch.Tensor, n_src: int, nq: int) -> Csr:
+    """CSR of an edge_index [2,E] (row 0 = source, row 1 = query); cached on the tensor object so the
+    GNO and the geometric embedding of one scale share it."""
+    cache = getattr(edge_index, "_gaot_csr", None)
+    if cache is not None and cache.n_src == n_src and cache.nq == nq and cache.E == edge_index.shape[1]:
+        return cache
+    csr = build_csr(edge_index[0], edge_index[1], n_src, nq, bool(getattr(edge_index, "_gaot_query_sorted", False)))
+    try:
+        edge_index._gaot_csr = csr
+    except Exception:
+        pass
+    return csr
+
+
+# ----------------------------------------------------------------------------- GNO
+_TRANSFORMS = {"linear": 0, "nonlinear": 1, "nonlinear_kernelonly": 2}
+
+
+def _mlp_desc(dims: Sequence[int]) -> MlpDesc:
+    d = MlpDesc()
+    d.n_layers = len(dims) - 1
+    if d.n_layers < 1 or d.n_layers > 6:
+        raise NotImplementedError("gno: the fused kernel supports 1..6 MLP layers")
+    for i, v in enumerate(dims):
+        d.dims[i] = int(v)
+    return d
+
+
+def _flat_params(weights, biases) -> torch.Tensor:
+    parts = []
+    for w, b in zip(weights, biases):
+        parts.append(w.reshape(-1))
+        parts.append(b.reshape(-1))
+    return torch.cat(parts).to(torch.float32).contiguous()
+
+
+class _GnoFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y_pos, x_pos, f_y, csr: Csr, dims, transform, reduce, precision, *wb):
+        nl = len(dims) - 1
+        weights, biases = wb[:nl], wb[nl:]
+        params = _flat_params(weights, biases)
+        dev = x_pos.device
+        lib = _lib_()
+        desc = _mlp_desc(dims)
+        nq, n_src, E = csr.nq, csr.n_src, csr.E
+        c_f = 0 if f_y is None else f_y.shape[1]
+        fy = None if f_y is None else f_y.detach().to(torch.float32).contiguous()
+        out = torch.empty(nq, dims[-1], dtype=torch.float32, device=dev)
+        wsb = lib.gaot_gno_workspace_bytes(E, nq, ctypes.byref(desc))
+        ws = _ws(wsb, dev)
+        with torch.cuda.device(dev):
+            check(lib.gaot_gno_forward(_p(y_pos), n_src, _p(x_pos), nq, _p(fy), c_f, _p(csr.rowptr), _p(csr.src),
+                                       _p(csr.qry), E, ctypes.byref(desc), _p(params), transform, reduce, precision,
+                                       _p(ws), wsb, _p(out), _stream(dev)), "gno_forward")
+        ctx.save_for_backward(y_pos, x_pos, fy, params)
+        ctx.csr, ctx.dims, ctx.transform, ctx.reduce, ctx.precision = csr, dims, transform, reduce, precision
+        ctx.need_f = f_y is not None and f_y.requires_grad
+        ctx.shapes = [(tuple(w.shape), tuple(b.shape)) for w, b in zip(weights, biases)]
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        y_pos, x_pos, fy, params = ctx.saved_tensors
+        csr, dims = ctx.csr, ctx.dims
+        dev = x_pos.device
+        lib = _lib_()
+        desc = _mlp_desc(dims)
+        d_out = d_out.to(torch.float32).contiguous()
+        d_params = torch.empty_like(params)
+        c_f = 0 if fy is None else fy.shape[1]
+        d_f = torch.empty_like(fy) if ctx.need_f else None
+        wsb = lib.gaot_gno_workspace_bytes(csr.E, csr.nq, ctypes.byref(desc))
+        ws = _ws(wsb, dev)
+        with torch.cuda.device(dev):
+            check(lib.gaot_gno_backward(_p(y_pos), csr.n_src, _p(x_pos), csr.nq, _p(fy), c_f, _p(csr.rowptr),
+                                        _p(csr.src), _p(csr.qry), csr.E, ctypes.byref(desc), _p(params),
+                                        ctx.transform, ctx.reduce, ctx.precision, _p(d_out), _p(ws), wsb,
+                                        _p(d_params), _p(d_f), _stream(dev)), "gno_backward")
+        gw, gb, off = [], [], 0
+        for (ws_, bs_) in ctx.shapes:
+            nw = ws_[0] * ws_[1]
+            gw.append(d_params[off: off + nw].view(ws_)); off += nw
+            gb.append(d_params[off: off + bs_[0]].view(bs_)); off += bs_[0]
+        return (None, None, d_f, None, None, None, None, None, *gw, *gb)
+
+
+def gno(y_pos, x_pos, f_y, csr: Csr, weights, biases, transform_type: str = "linear",
+        reduce: str = "mean", precision: Optional[str] = None) -> torch.Tensor:
+    """Fused gather -> kernel MLP -> (* f_y) -> segmented mean (reference integral_transform.py:114-171)."""
+    _need_cuda(y_pos, x_pos, f_y)
+    if f_y is None:
+        t = 3
+    else:
+        if transform_type not in _TRANSFORMS:
+            raise ValueError(f"unknown transform_type {transform_type}")
+        t = _TRANSFORMS[transform_type]
+    dims = [int(weights[0].shape[1])] + [int(w.shape[0]) for w in weights]
+    prec = _PRECISION["gno"] if precision is None else (0 if precision == "fp32" else 1)
+    return _GnoFn.apply(_pos3(y_pos), _pos3(x_pos), f_y, csr, tuple(dims), t, 0 if reduce == "mean" else 1, prec,
+                        *weights, *biases)
+
+
+# ----------------------------------------------------------------------------- geometric embedding
+def geo_stats(source_pos, query_pos, csr: Csr, normalize: bool = True) -> torch.Tensor:
+    """[nq, 9] statistical features (reference geoembed.py:99-182); z-scored over the queries when
+    `normalize` (the sharded encoder normalises after its all-reduce instead)."""
+    _need_cuda(source_pos, query_pos)
+    sp, qp = _pos3(source_pos), _pos3(query_pos)
+    dev = qp.device
+    lib = _lib_()
+    feat = torch.empty(csr.nq, 9, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.gaot_geo_stats(_p(sp), csr.n_src, _p(qp), csr.nq, _p(csr.rowptr), _p(csr.src), _p(feat),
+                                 _stream(dev)), "geo_stats")
+        if normalize:
+            zscore_(feat)
+    return feat
+
+
+def zscore_(feat: torch.Tensor) -> torch.Tensor:
+    _need_cuda(feat)
+    lib = _lib_()
+    dev = feat.device
+    wsb = lib.gaot_geo_zscore_workspace_bytes(feat.shape[0])
+    ws = _ws(wsb, dev)
+    with torch.cuda.device(dev):
+        check(lib.gaot_geo_zscore(_p(feat), feat.shape[0], feat.shape[1], _p(ws), wsb, _stream(dev)), "geo_zscore")
+    return feat
+
+
+# ----------------------------------------------------------------------------- attention
+class _AttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, num_heads, num_kv_heads, freqs):
+        lib = _lib_()
+        B, S, HD = q.shape
+        d = HD // num_heads
+        dev = q.device
+        q, k, v = (t.to(torch.float32).contiguous() for t in (q, k, v))
+        fr = None if freqs is None else freqs.detach().to(torch.float32).contiguous()
+        out = torch.empty(B, S, HD, dtype=torch.float32, device=dev)
+        lse = torch.empty(B, num_heads, S, dtype=torch.float32, device=dev)
+        wsb = lib.gaot_attn_workspace_bytes(B, S, num_heads, num_kv_heads, d)
+        ws = _ws(wsb, dev)
+        with torch.cuda.device(dev):
+            check(lib.gaot_attn_forward(_p(q), _p(k), _p(v), B, S, num_heads, num_kv_heads, d, _p(fr), _p(ws), wsb,
+                                        _p(out), _p(lse), _stream(dev)), "attn_forward")
+        ctx.save_for_backward(q, k, v, out, lse, fr)
+        ctx.cfg = (B, S, num_heads, num_kv_heads, d)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        q, k, v, out, lse, fr = ctx.saved_tensors
+        B, S, H, Hkv, d = ctx.cfg
+        lib = _lib_()
+        dev = q.device
+        d_out = d_out.to(torch.float32).contiguous()
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        wsb = lib.gaot_attn_workspace_bytes(B, S, H, Hkv, d)
+        ws = _ws(wsb, dev)
+        with torch.cuda.device(dev):
+            check(lib.gaot_attn_backward(_p(q), _p(k), _p(v), _p(out), _p(d_out), _p(lse), B, S, H, Hkv, d, _p(fr),
+                                         _p(ws), wsb, _p(dq), _p(dk), _p(dv), _stream(dev)), "attn_backward")
+        return dq, dk, dv, None, None, None
+
+
+def attention(q, k, v, num_heads: int, num_kv_heads: int, rope_freqs: Optional[torch.Tensor] = None):
+    """softmax(QK^T/sqrt(d))V on token-major projections q [B,S,H*d], k/v [B,S,Hkv*d]
+    (reference attn.py:110-128), optional 1-D RoPE with the module's `freqs`."""
+    _need_cuda(q, k, v)
+    return _AttnFn.apply(q, k, v, int(num_heads), int(num_kv_heads), rope_freqs)
+
+
+def launch_count() -> int:
+    return int(_lib_().gaot_launch_count())
+
+
+def reset_launch_count() -> None:
+    _lib_().gaot_launch_count_reset()

@@ -1,0 +1,180 @@
+/*
+ * gaot_b200.h -- C ABI of libgaot_b200.so: the B200 (sm_100a) hot path of GAOT-3D.
+ *
+ * The reference (Shizheng-Wen/GAOT-3D) is pure Python; it has no FFI layer.  Each
+ * entry point below replaces one third-party kernel call site of the reference
+ * (file:line relative to the reference root).  A maintainer binds them from
+ * Python with ctypes; gaot_3d_b200/_lib.py is that binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered,
+ *     nothing synchronises unless a *_host out-parameter is non-NULL;
+ *   - positions are float32 [n,3] row-major (D=2 inputs are zero-padded by the host);
+ *   - edge lists are int64 (the reference's edge_index dtype), CSR side-band is int32;
+ *   - return value: 0 = ok, otherwise a gaot_status code; gaot_last_error() gives text;
+ *   - no call allocates device memory: temporaries live in caller-provided workspaces
+ *     whose size comes from the matching *_workspace_bytes() function.
+ */
+#ifndef GAOT_B200_H
+#define GAOT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum gaot_status {
+    GAOT_OK = 0,
+    GAOT_ERR_INVALID = 1,      /* bad argument (shape / range / null) */
+    GAOT_ERR_WORKSPACE = 2,    /* workspace too small */
+    GAOT_ERR_CUDA = 3,         /* CUDA runtime error (see gaot_last_error) */
+    GAOT_ERR_UNSUPPORTED = 4   /* configuration outside the kernel envelope */
+};
+
+const char* gaot_last_error(void);
+int  gaot_abi_version(void);
+/* number of kernel launches issued by this library since load / last reset (bench.py gpu_launches) */
+int64_t gaot_launch_count(void);
+void gaot_launch_count_reset(void);
+
+/* ------------------------------------------------------------------ graph build
+ * Replaces torch_cluster.radius via torch_geometric.nn.radius
+ *   (reference src/model/layers/magno.py:193-200, :253-260).
+ * For every query y: all sources x with fp32 ((dx*dx+dy*dy)+dz*dz) < fl32(r*r),
+ * at most `cap` (PyG default 32), the FIRST `cap` by ascending x index, emitted
+ * grouped by ascending y, ascending x inside a group.
+ * Two phases: count (-> rowptr[ny+1], E) then emit (-> E edges); the workspace
+ * must be left untouched between the two calls.
+ */
+size_t gaot_radius_workspace_bytes(int64_t nx, int64_t ny);
+int gaot_radius_count(const float* x, int64_t nx, const float* y, int64_t ny,
+                      double r, int cap, void* ws, size_t ws_bytes,
+                      int32_t* rowptr /* [ny+1] out */, int64_t* E_host /* may be NULL */,
+                      void* stream);
+int gaot_radius_emit(const float* x, int64_t nx, const float* y, int64_t ny,
+                     double r, int cap, void* ws, size_t ws_bytes,
+                     const int32_t* rowptr, int64_t* out_y /* [E] */, int64_t* out_x /* [E] */,
+                     void* stream);
+
+/* Replaces torch_cluster.knn via torch_geometric.nn.knn (magno.py:183-189, :242-248).
+ * For every query y the k nearest sources x (same fp32 distance), ascending
+ * distance, ties -> lower x index.  Writes exactly ny*min(k,nx) edges grouped by y.
+ * k <= 128.
+ */
+size_t gaot_knn_workspace_bytes(int64_t nx, int64_t ny);
+int gaot_knn(const float* x, int64_t nx, const float* y, int64_t ny, int k,
+             void* ws, size_t ws_bytes, int64_t* out_y, int64_t* out_x, void* stream);
+
+/* Replaces torch_geometric.utils.coalesce (magno.py:220, :293): lexicographic
+ * (row0,row1) sort + duplicate removal of an int64 edge list.  Outputs are sized E_in
+ * by the caller; the unique count is written to *E_out_dev (device) and, when
+ * E_out_host != NULL, copied to the host (synchronises the stream).
+ */
+size_t gaot_coalesce_workspace_bytes(int64_t E_in);
+int gaot_coalesce(const int64_t* row0, const int64_t* row1, int64_t E_in,
+                  int64_t max_row0, int64_t max_row1,
+                  void* ws, size_t ws_bytes, int64_t* out0, int64_t* out1,
+                  int64_t* E_out_dev, int64_t* E_out_host, void* stream);
+
+/* Replaces torch_geometric.utils.dropout_edge (magno.py:367): keep[e] = u(e) >= p with a
+ * counter-based Philox stream (seed, offset); compacts both rows preserving order.
+ */
+size_t gaot_edge_mask_workspace_bytes(int64_t E_in);
+int gaot_edge_mask(const int64_t* row0, const int64_t* row1, int64_t E_in, double p_drop,
+                   uint64_t seed, uint64_t offset, void* ws, size_t ws_bytes,
+                   int64_t* out0, int64_t* out1, int64_t* E_out_dev, int64_t* E_out_host,
+                   void* stream);
+
+/* Query-major CSR side-band of an arbitrary-order edge list (precomputed int32/int64
+ * edges arrive in any order: magno.py:506-516, stat.py:191).  Stable: inside a query
+ * the original edge order is kept, so reductions are deterministic.
+ *   rowptr[nq+1], csr_src[E], csr_qry[E], perm[E] (original edge id of CSR slot)
+ */
+size_t gaot_csr_workspace_bytes(int64_t E, int64_t nq);
+int gaot_csr_from_edges(const int64_t* src, const int64_t* qry, int64_t E, int64_t n_src, int64_t nq,
+                        int flags /* bit0: edges already grouped by ascending qry (trusted hint) */,
+                        void* ws, size_t ws_bytes, int32_t* rowptr, int32_t* csr_src,
+                        int32_t* csr_qry, int32_t* perm, void* stream);
+
+/* ------------------------------------------------------------------ GNO (IntegralTransform)
+ * Replaces the gather -> cat -> LinearChannelMLP -> (* f_y) -> scatter(mean) chain of
+ *   reference src/model/layers/integral_transform.py:114-171 (torch index + cuBLAS +
+ *   torch_scatter) by one fused kernel.
+ *   out[q] = (1/max(cnt_q,1)) * sum_{e in CSR row q} MLP(cat[y_pos[src_e], x_pos[q] (,f_y[src_e])]) (* f_y[src_e])
+ * MLP: n_layers Linear layers, exact-erf GELU between them (mlp.py:327-335).
+ * `params` is one flat float32 buffer: for each layer W[out,in] row-major then b[out].
+ * transform: 0 = linear, 1 = nonlinear, 2 = nonlinear_kernelonly, 3 = kernel only (f_y == NULL).
+ * reduce: 0 = mean, 1 = raw sum (sharded encoder: partial sums, counts come from rowptr).
+ * precision: 0 = fp32 CUDA cores, 1 = bf16 operands / fp32 accumulate on tcgen05.
+ */
+typedef struct gaot_mlp_desc {
+    int32_t n_layers;        /* number of Linear layers, 1..6 */
+    int32_t dims[8];         /* dims[0] = input width, dims[l+1] = output width of layer l */
+} gaot_mlp_desc;
+
+size_t gaot_gno_workspace_bytes(int64_t E, int64_t nq, const gaot_mlp_desc* mlp);
+int gaot_gno_forward(const float* y_pos, int64_t n_src, const float* x_pos, int64_t nq,
+                     const float* f_y, int32_t c_f,
+                     const int32_t* rowptr, const int32_t* csr_src, const int32_t* csr_qry, int64_t E,
+                     const gaot_mlp_desc* mlp, const float* params,
+                     int transform, int reduce, int precision,
+                     void* ws, size_t ws_bytes, float* out /* [nq, dims[n_layers]] */, void* stream);
+/* Backward of the above: d_params (same flat layout as params), d_f_y [n_src, c_f] (may be NULL). */
+int gaot_gno_backward(const float* y_pos, int64_t n_src, const float* x_pos, int64_t nq,
+                      const float* f_y, int32_t c_f,
+                      const int32_t* rowptr, const int32_t* csr_src, const int32_t* csr_qry, int64_t E,
+                      const gaot_mlp_desc* mlp, const float* params,
+                      int transform, int reduce, int precision,
+                      const float* d_out, void* ws, size_t ws_bytes,
+                      float* d_params, float* d_f_y, void* stream);
+
+/* ------------------------------------------------------------------ geometric embedding statistics
+ * Replaces the 5 scatters + batched eigvalsh of reference src/model/layers/geoembed.py:99-175:
+ * per query [N_i, mean|y-x|, var|y-x|, centroid - x (3), eig(cov + 1e-6 I) descending (3)],
+ * zero rows for empty queries; `feat` is [nq, 9] BEFORE the global z-score (geoembed.py:177-180),
+ * which gaot_geo_zscore applies in place (unbiased std, std < 1e-6 -> 1).
+ */
+int gaot_geo_stats(const float* src_pos, int64_t n_src, const float* qry_pos, int64_t nq,
+                   const int32_t* rowptr, const int32_t* csr_src, float* feat, void* stream);
+size_t gaot_geo_zscore_workspace_bytes(int64_t nq);
+int gaot_geo_zscore(float* feat, int64_t nq, int32_t nfeat, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------ latent attention
+ * Replaces rotary_emb + F.scaled_dot_product_attention of reference
+ *   src/model/layers/attn.py:110-128.  q [B,S,H*d], k,v [B,S,Hkv*d] float32 (projection
+ *   outputs, token-major), out [B,S,H*d] float32.  d = 32 or 64, non-causal, no mask,
+ *   scale 1/sqrt(d), optional 1-D RoPE over the sequence index (theta 10000, interleaved pairs).
+ *   BF16 operands / FP32 accumulation on tcgen05 with TMEM accumulators.
+ *   lse [B,H,S] (log2 domain: max + log2(sum)) is saved for the backward.
+ */
+size_t gaot_attn_workspace_bytes(int64_t B, int64_t S, int32_t H, int32_t Hkv, int32_t d);
+int gaot_attn_forward(const float* q, const float* k, const float* v, int64_t B, int64_t S,
+                      int32_t H, int32_t Hkv, int32_t d,
+                      const float* rope_freqs /* [d/2] = RotaryEmbedding.freqs, NULL: no RoPE */,
+                      void* ws, size_t ws_bytes, float* out, float* lse, void* stream);
+int gaot_attn_backward(const float* q, const float* k, const float* v, const float* out,
+                       const float* d_out, const float* lse, int64_t B, int64_t S,
+                       int32_t H, int32_t Hkv, int32_t d, const float* rope_freqs,
+                       void* ws, size_t ws_bytes, float* dq, float* dk, float* dv, void* stream);
+
+/* ------------------------------------------------------------------ host-buffer convenience (e2e arm)
+ * Same graph build with HOST inputs/outputs: copies positions H2D, runs the kernels,
+ * copies the edge list D2H.  Returns E through *E_host; out rows sized by the caller
+ * (ny*cap for radius, ny*k for knn).
+ */
+int gaot_radius_host(const float* x_host, int64_t nx, const float* y_host, int64_t ny, double r, int cap,
+                     int64_t* out_y_host, int64_t* out_x_host, int64_t* E_host);
+int gaot_knn_host(const float* x_host, int64_t nx, const float* y_host, int64_t ny, int k,
+                  int64_t* out_y_host, int64_t* out_x_host, int64_t* E_host);
+
+/* tcgen05 self-test (layout / descriptor probe used by tests/test_tcgen05_probe.py):
+ * D[128,N] = A[128,K] * B[N,K]^T in bf16 with fp32 accumulate; variant selects operand majors. */
+int gaot_tc_probe(const float* A, const float* B, float* D, int N, int K, int variant, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAOT_B200_H */

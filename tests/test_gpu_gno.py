@@ -1,0 +1,149 @@
+"""GPU parity: fused GNO forward/backward and geometric-embedding kernels vs the CPU oracle and the
+golden vectors produced by the reference's own IntegralTransform / GeometricEmbedding.
+Tolerance (north star): rtol 1e-5 in FP32 (+ atol 1e-6*max|ref| for near-zero entries)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gno as ogno, graph as og
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda:0"
+
+
+def close(a, b, rtol=1e-5, atol_rel=2e-6, what=""):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    atol = atol_rel * max(b.abs().max().item(), 1e-30)
+    bad = (a - b).abs() > atol + rtol * b.abs()
+    assert not bad.any(), f"{what}: {int(bad.sum())}/{bad.numel()} off, max abs err {(a - b).abs().max().item():.3e} (ref max {b.abs().max().item():.3e})"
+
+
+@pytest.mark.parametrize("tag", ["enc", "dec"])
+def test_gno_golden_forward_backward(tag):
+    from gaot_3d_b200.layers import IntegralTransform
+    gld = torch.load(os.path.join(GOLD, "gno_golden.pt"))[tag]
+    it = IntegralTransform(channel_mlp_layers=gld["layers"]).to(DEV)
+    with torch.no_grad():
+        for fc, w, b in zip(it.channel_mlp.fcs, gld["weights"], gld["biases"]):
+            fc.weight.copy_(w); fc.bias.copy_(b)
+    f = gld["f_y"].to(DEV).requires_grad_(True)
+    out = it(gld["y_pos"].to(DEV), gld["x_pos"].to(DEV), gld["edge_index"].to(DEV), f)
+    close(out, gld["out"], what=f"{tag} forward")
+    out.backward(gld["d_out"].to(DEV))
+    # gradients accumulate over ~1e4 edges: compare at 2e-5 of the gradient scale
+    close(f.grad, gld["d_f"], rtol=2e-5, atol_rel=1e-5, what=f"{tag} d_f")
+    for i, fc in enumerate(it.channel_mlp.fcs):
+        close(fc.weight.grad, gld["d_weights"][i], rtol=1e-4, atol_rel=2e-5, what=f"{tag} dW{i}")
+        close(fc.bias.grad, gld["d_biases"][i], rtol=1e-4, atol_rel=2e-5, what=f"{tag} db{i}")
+
+
+@pytest.mark.parametrize("strategy,dec", [("knn", False), ("radius", False), ("bidirectional", True)])
+def test_gno_vs_oracle_larger(strategy, dec):
+    """32K-point cloud / 16^3 tokens: segments that span tiles, empty queries, long segments."""
+    from gaot_3d_b200 import ops
+    torch.manual_seed(0)
+    N, C = 32768, 32
+    phys, lat = synth.surface_cloud(N, seed=1), synth.latent_grid((16, 16, 16))
+    ei = torch.from_numpy(og.get_neighbor_strategy_np(strategy, phys, None, lat, None, 0.15, 2, dec, workers=-1))
+    ypos, xpos = (torch.from_numpy(lat), torch.from_numpy(phys)) if dec else (torch.from_numpy(phys), torch.from_numpy(lat))
+    layers = [6, 64, 64, C] if dec else [6, 64, 64, 64, C]
+    ws = [torch.randn(layers[i + 1], layers[i]) / np.sqrt(layers[i]) for i in range(len(layers) - 1)]
+    bs = [torch.randn(layers[i + 1]) * 0.1 for i in range(len(layers) - 1)]
+    f = torch.randn(ypos.shape[0], C)
+    ref = ogno.integral_transform(ypos.double(), xpos.double(), ei, f.double(), [w.double() for w in ws], [b.double() for b in bs])
+    ref32 = ogno.integral_transform(ypos, xpos, ei, f, ws, bs)
+    csr = ops.build_csr(ei[0].to(DEV), ei[1].to(DEV), ypos.shape[0], xpos.shape[0])
+    wd = [w.to(DEV).requires_grad_(True) for w in ws]
+    bd = [b.to(DEV).requires_grad_(True) for b in bs]
+    fd = f.to(DEV).requires_grad_(True)
+    out = ops.gno(ypos.to(DEV), xpos.to(DEV), fd, csr, wd, bd, precision="fp32")
+    # we must be as close to the fp64 truth as the reference's own fp32 evaluation is (x4 slack)
+    err_ours = (out.double().cpu() - ref).abs().max().item()
+    err_ref32 = (ref32.double() - ref).abs().max().item()
+    assert err_ours <= 4 * err_ref32 + 1e-7, (err_ours, err_ref32)
+    close(out, ref32, rtol=1e-5, atol_rel=4e-6, what="forward vs fp32 oracle")
+    # determinism: two runs bit-identical (no atomics in the forward)
+    out2 = ops.gno(ypos.to(DEV), xpos.to(DEV), fd, csr, wd, bd, precision="fp32")
+    assert torch.equal(out, out2)
+    # sum reduction (sharded-encoder partials) = mean * count
+    outs = ops.gno(ypos.to(DEV), xpos.to(DEV), fd, csr, wd, bd, reduce="sum", precision="fp32")
+    cnt = torch.bincount(ei[1], minlength=xpos.shape[0]).clamp(min=1).to(DEV)
+    close(outs / cnt[:, None], out, rtol=1e-6, what="sum vs mean")
+    # backward against fp64 autograd of the oracle
+    g = torch.randn_like(ref)
+    wr = [w.double().requires_grad_(True) for w in ws]
+    br = [b.double().requires_grad_(True) for b in bs]
+    fr = f.double().requires_grad_(True)
+    ogno.integral_transform(ypos.double(), xpos.double(), ei, fr, wr, br).backward(g)
+    out.backward(g.float().to(DEV))
+    close(fd.grad, fr.grad, rtol=2e-5, atol_rel=1e-5, what="d_f")
+    for i in range(len(ws)):
+        close(wd[i].grad, wr[i].grad, rtol=1e-4, atol_rel=3e-5, what=f"dW{i}")
+        close(bd[i].grad, br[i].grad, rtol=1e-4, atol_rel=3e-5, what=f"db{i}")
+
+
+def test_gno_edge_cases():
+    from gaot_3d_b200.layers import IntegralTransform
+    it = IntegralTransform(channel_mlp_layers=[6, 64, 32]).to(DEV)
+    y, x = torch.rand(100, 3, device=DEV), torch.rand(50, 3, device=DEV)
+    f = torch.randn(100, 32, device=DEV)
+    out = it(y, x, torch.empty(2, 0, dtype=torch.long, device=DEV), f)
+    assert out.shape == (50, 32) and float(out.abs().max()) == 0.0
+    # int32 edges in arbitrary order (precomputed-edge path, stat.py:191) + one edge + ragged segments
+    ei = torch.tensor([[5, 7, 7, 99, 0], [49, 0, 49, 3, 0]], dtype=torch.int32, device=DEV)
+    out = it(y, x, ei, f)
+    ref = ogno.integral_transform(y.cpu(), x.cpu(), ei.long().cpu(), f.cpu(), [fc.weight.detach().cpu() for fc in it.channel_mlp.fcs],
+                                  [fc.bias.detach().cpu() for fc in it.channel_mlp.fcs])
+    close(out, ref, what="tiny ragged")
+    # kernel-only transform and f_y=None
+    it2 = IntegralTransform(channel_mlp_layers=[6 + 32, 64, 16], transform_type="nonlinear_kernelonly").to(DEV)
+    out = it2(y, x, ei, f)
+    ref = ogno.integral_transform(y.cpu(), x.cpu(), ei.long().cpu(), f.cpu(), [fc.weight.detach().cpu() for fc in it2.channel_mlp.fcs],
+                                  [fc.bias.detach().cpu() for fc in it2.channel_mlp.fcs], transform_type="nonlinear_kernelonly")
+    close(out, ref, what="nonlinear_kernelonly")
+    it3 = IntegralTransform(channel_mlp_layers=[6 + 32, 64, 32], transform_type="nonlinear").to(DEV)
+    fg = f.clone().requires_grad_(True)
+    out = it3(y, x, ei, fg)
+    fr = f.detach().cpu().double().requires_grad_(True)
+    ref = ogno.integral_transform(y.cpu().double(), x.cpu().double(), ei.long().cpu(), fr,
+                                  [fc.weight.detach().cpu().double() for fc in it3.channel_mlp.fcs],
+                                  [fc.bias.detach().cpu().double() for fc in it3.channel_mlp.fcs], transform_type="nonlinear")
+    close(out, ref, what="nonlinear")
+    g = torch.randn(50, 32)
+    ref.backward(g.double()); out.backward(g.to(DEV))
+    close(fg.grad, fr.grad, rtol=2e-5, atol_rel=1e-5, what="nonlinear d_f")
+    out = it(y, x, ei, None) if False else None     # f_y=None needs an MLP with matching width; covered below
+    it4 = IntegralTransform(channel_mlp_layers=[6, 32, 8]).to(DEV)
+    out = it4(y, x, ei, None)
+    ref = ogno.integral_transform(y.cpu(), x.cpu(), ei.long().cpu(), None, [fc.weight.detach().cpu() for fc in it4.channel_mlp.fcs],
+                                  [fc.bias.detach().cpu() for fc in it4.channel_mlp.fcs])
+    close(out, ref, what="f_y=None")
+
+
+def test_geo_golden_and_oracle():
+    from gaot_3d_b200.layers import GeometricEmbedding
+    gld = torch.load(os.path.join(GOLD, "geo_golden.pt"))
+    ge = GeometricEmbedding(3, 32).to(DEV)
+    ge.load_state_dict(gld["state"])
+    src, qry, ei = gld["source_pos"].to(DEV), gld["query_pos"].to(DEV), gld["edge_index"].to(DEV)
+    feats = ge.statistical_features(src, qry, ei)
+    # the smallest covariance eigenvalue is ill-conditioned in the reference's own fp32 eigvalsh; compare
+    # against the fp64 evaluation of the same formulas with the fp32 reference's error as the yardstick
+    ref64 = ogno.geo_statistical_features(gld["source_pos"].double(), gld["query_pos"].double(), gld["edge_index"])
+    err_ours = (feats.double().cpu() - ref64).abs().max(dim=0).values
+    err_ref = (gld["features"].double() - ref64).abs().max(dim=0).values
+    assert bool((err_ours <= 4 * err_ref + 1e-5).all()), (err_ours, err_ref)
+    emb = ge(src, qry, ei)
+    close(emb, gld["embedding"], rtol=1e-4, atol_rel=1e-4, what="embedding vs reference fp32")
+    # un-normalised features, bigger cloud, includes empty queries
+    phys, lat = synth.surface_cloud(32768, seed=4), synth.latent_grid((16, 16, 16))
+    ei = torch.from_numpy(og.radius_np(phys, lat, 0.15, workers=-1)[::-1].copy())
+    raw = ge.statistical_features(torch.from_numpy(phys).to(DEV), torch.from_numpy(lat).to(DEV), ei.to(DEV), normalize=False)
+    ref = ogno.geo_statistical_features(torch.from_numpy(phys).double(), torch.from_numpy(lat).double(), ei, normalize=False)
+    close(raw[:, :6], ref[:, :6], rtol=1e-4, atol_rel=1e-5, what="moments")
+    close(raw[:, 6:], ref[:, 6:], rtol=1e-3, atol_rel=1e-4, what="eigenvalues")
+    assert float(raw[(ref[:, 0] == 0).to(DEV)].abs().max()) == 0.0
