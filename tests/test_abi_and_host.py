@@ -1,0 +1,90 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/gaot_b200.h declares (no compute without a GPU), host-side logic and error behaviour."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from gaot_3d_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def test_exports_match_header(lib):
+    from gaot_3d_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "gaot_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(gaot_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.gaot_abi_version() == 1
+    # size queries are pure host arithmetic
+    assert lib.gaot_radius_workspace_bytes(500000, 131072) > 0
+    assert lib.gaot_attn_workspace_bytes(1, 16384, 8, 8, 32) > 0
+
+
+def test_no_cpu_fallback():
+    import gaot_3d_b200 as G
+    p = torch.rand(10, 3)
+    with pytest.raises(RuntimeError, match="GPU only|no CPU fallback"):
+        G.get_neighbor_strategy("knn", p, None, p, None, 0.1)
+    it = G.IntegralTransform(channel_mlp_layers=[6, 8, 4])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        it(p, p, torch.zeros(2, 3, dtype=torch.long), torch.rand(10, 4))
+    # the reference's zero-edge early-out needs no kernel and keeps working
+    assert it(p, p, torch.empty(2, 0, dtype=torch.long), None).shape == (10, 4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        G.ops.attention(torch.rand(1, 8, 64), torch.rand(1, 8, 64), torch.rand(1, 8, 64), 2, 2)
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under gaot_3d_b200/ may reference it."""
+    for dp, _, fs in os.walk(os.path.join(ROOT, "gaot_3d_b200")):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dp, f)
+                assert "/root/reference" not in src, os.path.join(dp, f)
+
+
+def test_host_logic():
+    import gaot_3d_b200 as G
+    from gaot_3d_b200.graph import apply_neighbor_sampling, parse_geoembed_strategy, _example_slices
+    assert G.parse_neighbor_strategy("knn") == ("knn", "knn")
+    assert G.parse_neighbor_strategy(["radius", "reverse"]) == ("radius", "reverse")
+    with pytest.raises(ValueError):
+        G.parse_neighbor_strategy(["a", "b", "c"])
+    assert parse_geoembed_strategy([True, False]) == (True, False)
+    with pytest.raises(ValueError):
+        parse_geoembed_strategy("yes")
+    ei = torch.tensor([[0, 1, 2, 3, 4, 5], [0, 0, 0, 1, 1, 2]])
+    assert apply_neighbor_sampling(ei, 3, None, None) is ei
+    assert apply_neighbor_sampling(ei, 3, None, "ratio", sample_ratio=1.0) is ei
+    assert apply_neighbor_sampling(ei, 3, None, "ratio", sample_ratio=0.5, training=False) is ei
+    out = apply_neighbor_sampling(ei, 3, torch.device("cpu"), "max_neighbors", max_neighbors=2)
+    assert torch.bincount(out[1], minlength=3).tolist() == [2, 2, 1]
+    with pytest.raises(ValueError):
+        apply_neighbor_sampling(ei, 3, None, "bogus")
+    with pytest.raises(ValueError):
+        apply_neighbor_sampling(ei, 3, None, "ratio")
+    b = torch.tensor([0, 0, 1, 1, 1, 3])
+    assert _example_slices(b, 6, 4) == [(0, 2), (2, 5), (5, 5), (5, 6)]
+    # module shells: error behaviour of the reference
+    mc = G.MAGNOConfig(gno_coord_dim=3, lifting_channels=8, mlp_type="linear", use_geoembed=False, precompute_edges=True)
+    enc = G.MAGNOEncoder(3, 8, mc)
+    bt = G.Batch(pos=torch.rand(5, 3), x=torch.rand(5, 3))
+    with pytest.raises(AttributeError, match="encoder_edge_index_s0"):
+        enc(bt, torch.rand(8, 3), torch.zeros(8, dtype=torch.long))
+    mc2 = G.MAGNOConfig(gno_coord_dim=3, lifting_channels=8, mlp_type="linear", use_geoembed=False, encoder_feature_attr="nope")
+    with pytest.raises(AttributeError, match="nope"):
+        G.MAGNOEncoder(3, 8, mc2)(bt, torch.rand(8, 3), torch.zeros(8, dtype=torch.long))
+    with pytest.raises(ValueError):
+        G.init_model(3, 1, "other")

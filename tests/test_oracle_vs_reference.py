@@ -1,0 +1,111 @@
+"""Pins the travelling torch restatements (oracle/gno.py, oracle/attn.py, oracle/model.py) against
+(a) the reference's own modules imported from /root/reference (dev container only) and
+(b) the committed golden vectors those modules produced (everywhere).  Pure CPU."""
+import os
+
+import pytest
+import torch
+
+from oracle import attn as oattn, gno as ogno, model as omodel, ref_loader
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+needs_ref = pytest.mark.skipif(not ref_loader.reference_available(), reason="/root/reference not present")
+
+
+def test_gno_golden():
+    for tag, g in torch.load(os.path.join(GOLD, "gno_golden.pt")).items():
+        ws = [w.clone().requires_grad_(True) for w in g["weights"]]
+        bs = [b.clone().requires_grad_(True) for b in g["biases"]]
+        f = g["f_y"].clone().requires_grad_(True)
+        out = ogno.integral_transform(g["y_pos"], g["x_pos"], g["edge_index"], f, ws, bs)
+        assert torch.allclose(out, g["out"], rtol=1e-5, atol=1e-7), tag
+        out.backward(g["d_out"])
+        assert torch.allclose(f.grad, g["d_f"], rtol=1e-4, atol=1e-6)
+        for a, b in zip(ws, g["d_weights"]):
+            assert torch.allclose(a.grad, b, rtol=1e-3, atol=1e-5 * b.abs().max().item())
+
+
+def test_geo_golden():
+    g = torch.load(os.path.join(GOLD, "geo_golden.pt"))
+    feats = ogno.geo_statistical_features(g["source_pos"], g["query_pos"], g["edge_index"])
+    assert torch.allclose(feats, g["features"], rtol=1e-4, atol=1e-5)
+    s = g["state"]
+    emb = ogno.geo_embedding(g["source_pos"], g["query_pos"], g["edge_index"], s["mlp.0.weight"], s["mlp.0.bias"],
+                             s["mlp.2.weight"], s["mlp.2.bias"])
+    assert torch.allclose(emb, g["embedding"], rtol=1e-4, atol=1e-5)
+
+
+def test_attention_golden():
+    for tag, g in torch.load(os.path.join(GOLD, "attn_golden.pt")).items():
+        s = g["state"]
+        x = g["x"]
+        lin = torch.nn.functional.linear
+        o = oattn.attention_core(lin(x, s["q_proj.weight"]), lin(x, s["k_proj.weight"]), lin(x, s["v_proj.weight"]),
+                                 g["num_heads"], g["num_kv_heads"], g["rope"])
+        assert torch.allclose(lin(o, s["o_proj.weight"]), g["out"], rtol=1e-4, atol=1e-6), tag
+
+
+def test_model_golden():
+    for tag, g in torch.load(os.path.join(GOLD, "model_golden.pt")).items():
+        strat = g["strategy"]
+        es, ds = (strat, strat) if isinstance(strat, str) else strat
+        nkv = g["state"]["processor.encoder_layers.0.attn.k_proj.weight"].shape[0] // 32
+        cfg = dict(latent_tokens=tuple(g["latent_tokens"]), patch_size=2, lifting_channels=32, radius=g["radius"], k=g["k"],
+                   enc_strategy=es, dec_strategy=ds, use_geoembed=g["use_geoembed"], num_layers=3, num_heads=4,
+                   num_kv_heads=nkv, norm_eps=1e-6, positional_embedding="rope")
+        y = omodel.gaot3d_forward(g["state"], cfg, g["pos"], [g["pos"], g["c"]], latent_pos=g["tokens_pos"])
+        assert torch.allclose(y, g["out"], rtol=1e-4, atol=1e-6), tag
+
+
+@needs_ref
+def test_restatements_match_reference_modules():
+    ref = ref_loader.load_reference()
+    torch.manual_seed(0)
+    y, x = torch.rand(800, 3) * 2 - 1, torch.rand(200, 3) * 2 - 1
+    ei = torch.stack([torch.randint(0, 800, (5000,)), torch.randint(0, 200, (5000,))])
+    for tt in ("linear", "nonlinear", "nonlinear_kernelonly"):
+        kin = 6 + (16 if tt != "linear" else 0)
+        it = ref.integral_transform.IntegralTransform(channel_mlp_layers=[kin, 32, 16], transform_type=tt)
+        f = torch.randn(800, 16)
+        a = it(y, x, ei, f)
+        b = ogno.integral_transform(y, x, ei, f, [l.weight for l in it.channel_mlp.fcs], [l.bias for l in it.channel_mlp.fcs], tt)
+        assert torch.allclose(a, b, rtol=1e-6, atol=1e-7), tt
+    ge = ref.geoembed.GeometricEmbedding(3, 8)
+    a = ge._compute_statistical_features_pyg(y, x, ei)
+    assert torch.allclose(a, ogno.geo_statistical_features(y, x, ei), rtol=1e-5, atol=1e-6)
+    # scatter_native mean with empty segments
+    src, idx = torch.randn(50, 4), torch.randint(0, 9, (50,))
+    assert torch.allclose(ref.scatter_native.scatter_native(src, idx, dim=0, dim_size=12, reduce="mean"), ogno.scatter_mean(src, idx, 12))
+
+
+@needs_ref
+def test_config_schema_and_state_dict_keys_match_reference():
+    """Drop-in boundary: dataclass fields/defaults and parameter names are the schema."""
+    import dataclasses
+    import gaot_3d_b200 as G
+    ref = ref_loader.load_reference()
+    for ours, theirs in ((G.MAGNOConfig, ref.magno.MAGNOConfig), (G.TransformerConfig, ref.attn.TransformerConfig),
+                         (G.AttentionConfig, ref.attn.AttentionConfig), (G.FFNConfig, ref.attn.FFNConfig)):
+        fo = {f.name: f for f in dataclasses.fields(ours)}
+        ft = {f.name: f for f in dataclasses.fields(theirs)}
+        assert list(fo) == list(ft), ours.__name__
+        a, b = ours(), theirs()
+        for n in fo:
+            va, vb = getattr(a, n), getattr(b, n)
+            if dataclasses.is_dataclass(va):
+                continue
+            assert va == vb, (ours.__name__, n, va, vb)
+    for strat, geo, mlp in ((["radius", "reverse"], [True, False], "linear"), ("bidirectional", [True, True], "channel")):
+        kw = dict(gno_coord_dim=3, lifting_channels=16, neighbor_strategy=strat, use_geoembed=geo, mlp_type=mlp,
+                  encoder_feature_attr=["pos", "c"], use_scale_weights=True, scales=[1.0, 2.0])
+        for pe, nl in (("rope", 3), ("absolute", 4)):
+            tr, to = ref.attn.TransformerConfig(patch_size=2, hidden_size=64, num_layers=nl, positional_embedding=pe), \
+                     G.TransformerConfig(patch_size=2, hidden_size=64, num_layers=nl, positional_embedding=pe)
+            for t in (tr, to):
+                t.attn_config.hidden_size, t.ffn_config.hidden_size = 64, 96
+            mr = ref.gaot_3d.GAOT3D(6, 4, ref.magno.MAGNOConfig(**kw), tr, latent_tokens=(4, 4, 4))
+            mo = G.GAOT3D(6, 4, G.MAGNOConfig(**kw), to, latent_tokens=(4, 4, 4))
+            sr, so = mr.state_dict(), mo.state_dict()
+            assert list(sr) == list(so)
+            assert all(sr[k].shape == so[k].shape for k in sr)
+            mo.load_state_dict(sr, strict=True)
