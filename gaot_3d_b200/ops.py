@@ -32,6 +32,42 @@ def _lib_():
     return _lib.load()
 
 
+# ---- optional per-op device timing (bench.py): CUDA events on the launching stream ----
+_TIMING = {"on": False, "events": []}
+
+
+def enable_timing(on: bool = True) -> None:
+    _TIMING["on"] = on
+    _TIMING["events"] = []
+
+
+class _timed:
+    def __init__(self, name, dev):
+        self.name, self.dev = name, dev
+
+    def __enter__(self):
+        if _TIMING["on"]:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record(torch.cuda.current_stream(self.dev))
+        return self
+
+    def __exit__(self, *a):
+        if _TIMING["on"]:
+            self.e.record(torch.cuda.current_stream(self.dev))
+            _TIMING["events"].append((self.name, self.s, self.e))
+        return False
+
+
+def timing_summary() -> dict:
+    """name -> (calls, total ms); call after torch.cuda.synchronize()."""
+    out = {}
+    for name, s, e in _TIMING["events"]:
+        c, t = out.get(name, (0, 0.0))
+        out[name] = (c + 1, t + s.elapsed_time(e))
+    return out
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -77,7 +113,7 @@ def radius(x: torch.Tensor, y: torch.Tensor, r: float, max_num_neighbors: int = 
     ws = _ws(wsb, dev)
     rowptr = torch.empty(ny + 1, dtype=torch.int32, device=dev)
     E = ctypes.c_int64(0)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _timed("radius", dev):
         check(lib.gaot_radius_count(_p(x), nx, _p(y), ny, float(r), int(max_num_neighbors), _p(ws), wsb,
                                     _p(rowptr), ctypes.byref(E), _stream(dev)), "radius_count")
         out_y = torch.empty(E.value, dtype=torch.long, device=dev)
@@ -103,7 +139,7 @@ def knn(x: torch.Tensor, y: torch.Tensor, k: int):
     ws = _ws(wsb, dev)
     out_y = torch.empty(ny * k, dtype=torch.long, device=dev)
     out_x = torch.empty(ny * k, dtype=torch.long, device=dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _timed("knn", dev):
         check(lib.gaot_knn(_p(x), nx, _p(y), ny, k, _p(ws), wsb, _p(out_y), _p(out_x), _stream(dev)), "knn")
     return out_y, out_x
 
@@ -231,7 +267,7 @@ class _GnoFn(torch.autograd.Function):
         out = torch.empty(nq, dims[-1], dtype=torch.float32, device=dev)
         wsb = lib.gaot_gno_workspace_bytes(E, nq, ctypes.byref(desc))
         ws = _ws(wsb, dev)
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), _timed("gno_fwd", dev):
             check(lib.gaot_gno_forward(_p(y_pos), n_src, _p(x_pos), nq, _p(fy), c_f, _p(csr.rowptr), _p(csr.src),
                                        _p(csr.qry), E, ctypes.byref(desc), _p(params), transform, reduce, precision,
                                        _p(ws), wsb, _p(out), _stream(dev)), "gno_forward")
@@ -254,7 +290,7 @@ class _GnoFn(torch.autograd.Function):
         d_f = torch.empty_like(fy) if ctx.need_f else None
         wsb = lib.gaot_gno_workspace_bytes(csr.E, csr.nq, ctypes.byref(desc))
         ws = _ws(wsb, dev)
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), _timed("gno_bwd", dev):
             check(lib.gaot_gno_backward(_p(y_pos), csr.n_src, _p(x_pos), csr.nq, _p(fy), c_f, _p(csr.rowptr),
                                         _p(csr.src), _p(csr.qry), csr.E, ctypes.byref(desc), _p(params),
                                         ctx.transform, ctx.reduce, ctx.precision, _p(d_out), _p(ws), wsb,
@@ -325,7 +361,7 @@ class _AttnFn(torch.autograd.Function):
         lse = torch.empty(B, num_heads, S, dtype=torch.float32, device=dev)
         wsb = lib.gaot_attn_workspace_bytes(B, S, num_heads, num_kv_heads, d)
         ws = _ws(wsb, dev)
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), _timed("attn_fwd", dev):
             check(lib.gaot_attn_forward(_p(q), _p(k), _p(v), B, S, num_heads, num_kv_heads, d, _p(fr), _p(ws), wsb,
                                         _p(out), _p(lse), _stream(dev)), "attn_forward")
         ctx.save_for_backward(q, k, v, out, lse, fr)
@@ -342,7 +378,7 @@ class _AttnFn(torch.autograd.Function):
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
         wsb = lib.gaot_attn_workspace_bytes(B, S, H, Hkv, d)
         ws = _ws(wsb, dev)
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), _timed("attn_bwd", dev):
             check(lib.gaot_attn_backward(_p(q), _p(k), _p(v), _p(out), _p(d_out), _p(lse), B, S, H, Hkv, d, _p(fr),
                                          _p(ws), wsb, _p(dq), _p(dk), _p(dv), _stream(dev)), "attn_backward")
         return dq, dk, dv, None, None, None
