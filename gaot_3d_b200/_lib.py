@@ -25,6 +25,8 @@ _SIGS = {
     "gaot_abi_version": (c_int, []),
     "gaot_launch_count": (c_int64, []),
     "gaot_launch_count_reset": (None, []),
+    "gaot_profile_enable": (None, [c_int]),
+    "gaot_profile_summary": (c_int, [c_char_p, c_size_t]),
     "gaot_radius_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "gaot_radius_count": (c_int, [P, c_int64, P, c_int64, c_double, c_int, P, c_size_t, P, POINTER(c_int64), P]),
     "gaot_radius_emit": (c_int, [P, c_int64, P, c_int64, c_double, c_int, P, c_size_t, P, P, P, P]),

@@ -3,6 +3,9 @@
 #include <atomic>
 #include <cstdarg>
 #include <mutex>
+#include <vector>
+#include <map>
+#include <string>
 
 namespace gaot {
 static thread_local char g_err[1024] = "";
@@ -14,6 +17,23 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+struct ProfRec { const char* name; cudaEvent_t e0, e1; double work; };
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+
+KernelTimer::KernelTimer(const char* n, cudaStream_t s, double w) : name(n), st(s), work(w) {
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { e0 = e1 = nullptr; return; }
+    cudaEventRecord(e0, st);
+}
+KernelTimer::~KernelTimer() {
+    if (!e0) return;
+    cudaEventRecord(e1, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back({name, e0, e1, work});
+}
 }  // namespace gaot
 
 using namespace gaot;
@@ -24,6 +44,35 @@ const char* gaot_last_error(void) { return g_err; }
 int gaot_abi_version(void) { return 1; }
 int64_t gaot_launch_count(void) { return g_launches.load(); }
 void gaot_launch_count_reset(void) { g_launches.store(0); }
+
+void gaot_profile_enable(int on) {
+    g_prof_on.store(on ? 1 : 0);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    g_prof.clear();
+}
+
+// "name calls total_ms total_work\n" per kernel; synchronises on the recorded events.
+int gaot_profile_summary(char* buf, size_t buf_bytes) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    struct Acc { int64_t calls = 0; double ms = 0, work = 0; };
+    std::map<std::string, Acc> acc;
+    for (auto& r : g_prof) {
+        if (cudaEventSynchronize(r.e1) != cudaSuccess) { set_error("profile: event sync failed"); return GAOT_ERR_CUDA; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        Acc& a = acc[r.name]; a.calls++; a.ms += ms; a.work += r.work;
+    }
+    std::string out;
+    char line[256];
+    for (auto& kv : acc) {
+        snprintf(line, sizeof(line), "%s %lld %.6f %.6e\n", kv.first.c_str(), (long long)kv.second.calls, kv.second.ms, kv.second.work);
+        out += line;
+    }
+    if (out.size() + 1 > buf_bytes) { set_error("profile: buffer too small"); return GAOT_ERR_INVALID; }
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return GAOT_OK;
+}
 
 // Host-buffer graph build: H2D copy of positions, kernels, D2H copy of the edge list.
 int gaot_radius_host(const float* x_host, int64_t nx, const float* y_host, int64_t ny, double r, int cap,

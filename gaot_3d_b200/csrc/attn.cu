@@ -490,6 +490,7 @@ int gaot_attn_forward(const float* q, const float* k, const float* v, int64_t B,
     if (rc) return rc;
     const float scale_log2 = (1.0f / sqrtf((float)d)) * 1.4426950408889634f;
     dim3 grid((unsigned)((S + 127) / 128), (unsigned)H, (unsigned)B);
+    GAOT_TIME_KERNEL("attn_fwd", st, 4.0 * (double)B * H * (double)S * (double)S * d);
     if (d == 32) {
         const size_t smem = 5 * 128 * 32 * 2 + 128 * 128 * 2;
         GAOT_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -519,6 +520,8 @@ int gaot_attn_backward(const float* q, const float* k, const float* v, const flo
     GAOT_CUDA(cudaMemsetAsync(w.dQacc, 0, (size_t)B * H * S * d * sizeof(float), st));
     const float scale = 1.0f / sqrtf((float)d), scale_log2 = scale * 1.4426950408889634f;
     dim3 grid((unsigned)((S + 127) / 128), (unsigned)H, (unsigned)B);
+    {
+    GAOT_TIME_KERNEL("attn_bwd", st, 10.0 * (double)B * H * (double)S * (double)S * d);
     if (d == 32) {
         const size_t smem = 4 * 128 * 32 * 2 + 2 * 128 * 128 * 2;
         GAOT_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -529,6 +532,7 @@ int gaot_attn_backward(const float* q, const float* k, const float* v, const flo
         GAOT_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attn_bwd_kernel<64><<<grid, 256, smem, st>>>(w.Qb, w.Kb, w.Vb, w.dOb, lse, w.Dvec, w.dQacc, w.dKh, w.dVh,
                                                      (int)S, H, Hkv, scale, scale_log2);
+    }
     }
     GAOT_LAUNCH_CHECK();
     attn_bwd_post_kernel<<<nb256(B * S * H * (d / 8)), 256, 0, st>>>(w.dQacc, dq, B, S, H, H, d, rope_freqs);

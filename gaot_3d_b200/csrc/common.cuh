@@ -25,6 +25,15 @@ void count_launch(int n = 1);
         gaot::set_error("%s:%d kernel launch failed: %s", __FILE__, __LINE__,             \
                         cudaGetErrorString(_e)); return GAOT_ERR_CUDA; } } while (0)
 
+// Optional device-side timing of the main kernels (bench.py roofline): CUDA events recorded on
+// the launching stream around the launch, read back by gaot_profile_summary().
+struct KernelTimer {
+    const char* name; cudaStream_t st; cudaEvent_t e0 = nullptr, e1 = nullptr; double work;
+    KernelTimer(const char* name, cudaStream_t st, double work = 0.0);
+    ~KernelTimer();
+};
+#define GAOT_TIME_KERNEL(name, st, work) gaot::KernelTimer _gaot_kt(name, st, work)
+
 constexpr int kNumSMs = 148;   // B200
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }

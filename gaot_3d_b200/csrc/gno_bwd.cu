@@ -380,6 +380,8 @@ int gno_backward_fp32(const GnoArgs& a_in, const float* d_out, void* ws, size_t 
     const BwdSmemLayout L = bwd_layout(a);
     const size_t smem = (size_t)L.total_floats * sizeof(float);
     if (smem > 227 * 1024) { set_error("gno_backward: MLP too large for shared memory (%zu B)", smem); return GAOT_ERR_UNSUPPORTED; }
+    const int CoutB = a.dims[a.n_layers];
+    GAOT_TIME_KERNEL("gno_bwd", st, (double)a.E * (16.0 + 12.0 + 4.0 * a.c_f) + (double)a.nq * (12.0 + 8.0 * CoutB) + (double)a.n_src * 4.0 * a.c_f);
 #define GAOT_BWD_CASE(NL)                                                                                   \
     case NL:                                                                                                \
         GAOT_CUDA(cudaFuncSetAttribute(gno_bwd_fp32_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \

@@ -255,7 +255,11 @@ int gno_forward_fp32(const GnoArgs& a, void* ws, size_t ws_bytes, float* out, cu
     if (smem > 227 * 1024) { set_error("gno_forward: MLP too large for shared memory (%zu B)", smem); return GAOT_ERR_UNSUPPORTED; }
     GAOT_CUDA(cudaFuncSetAttribute(gno_fwd_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = a.ntiles < kNumSMs ? a.ntiles : kNumSMs;
-    gno_fwd_fp32_kernel<<<grid, FTHREADS, smem, st>>>(a, L, out, head_partial);
+    {
+        // algorithmic bytes: E*(16 + 4D + 4C_f) + nq*(4D + 4C_out)
+        GAOT_TIME_KERNEL("gno_fwd", st, (double)a.E * (16.0 + 12.0 + 4.0 * a.c_f) + (double)a.nq * (12.0 + 4.0 * Cout));
+        gno_fwd_fp32_kernel<<<grid, FTHREADS, smem, st>>>(a, L, out, head_partial);
+    }
     GAOT_LAUNCH_CHECK();
     if (a.ntiles > 1) {
         gno_fwd_fixup_kernel<<<a.ntiles - 1, 64, 0, st>>>(a, out, head_partial);

@@ -379,6 +379,7 @@ int gaot_knn(const float* x, int64_t nx, const float* y, int64_t ny, int k, void
     int rc = build_cells(x, nx, y, ny, 0.f, 1, w, st);
     if (rc) return rc;
     const unsigned nb = nblk(ny, 128);
+    GAOT_TIME_KERNEL("knn_search", st, 24.0 * (double)(nx + ny) + 8.0 * (double)(nx + ny) + 16.0 * (double)ny * k);
     if (k == 1)       knn_kernel<1><<<nb, 128, 0, st>>>(y, ny, w.qperm, w.gp, w.cell_start, w.pts, k, out_y, out_x);
     else if (k <= 8)  knn_kernel<8><<<nb, 128, 0, st>>>(y, ny, w.qperm, w.gp, w.cell_start, w.pts, k, out_y, out_x);
     else if (k <= 32) knn_kernel<32><<<nb, 128, 0, st>>>(y, ny, w.qperm, w.gp, w.cell_start, w.pts, k, out_y, out_x);

@@ -39,6 +39,11 @@ int  gaot_abi_version(void);
 /* number of kernel launches issued by this library since load / last reset (bench.py gpu_launches) */
 int64_t gaot_launch_count(void);
 void gaot_launch_count_reset(void);
+/* optional CUDA-event timing of the main kernels on their launching stream; summary lines are
+ * "kernel_name calls total_ms total_algorithmic_work" (work = bytes for HBM-bound kernels, FLOPs
+ * for tensor-bound ones).  enable(on) also clears the records. */
+void gaot_profile_enable(int on);
+int gaot_profile_summary(char* buf, size_t buf_bytes);
 
 /* ------------------------------------------------------------------ graph build
  * Replaces torch_cluster.radius via torch_geometric.nn.radius
