@@ -18,6 +18,7 @@
 //            with vector reductions.
 #include "common.cuh"
 #include "tc05.cuh"
+#include <cstdlib>
 
 namespace gaot {
 
@@ -125,18 +126,36 @@ __device__ __forceinline__ void store_row(uint8_t* tile, int row, const uint4 (&
 }
 
 // --------------------------------------------------------------------------- forward
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// V tiles carry 16 extra columns: column D is all ones, so the P*V tensor-core product also
+// returns the row sum of the (bf16-rounded) probabilities -- no per-element FADD in the softmax.
+// Software pipeline (one mbarrier wait + one CTA barrier per key tile): after the softmax of tile j
+// the issuing thread queues P_j*V_j AND S_{j+1} = Q K_{j+1}^T back to back; the O update with the
+// P_{j-1}*V_{j-1} result is deferred to the top of the next iteration.
 template <int D>
 __global__ void __launch_bounds__(128, 2)
 attn_fwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const bf16* __restrict__ Vb,
                 float* __restrict__ out, float* __restrict__ lse, int S, int H, int Hkv, float scale_log2) {
     extern __shared__ __align__(1024) uint8_t sm[];
-    __shared__ uint64_t mbar[2];
+    __shared__ uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
     constexpr int TILE_B = 128 * D * 2;
+    constexpr int VTILE_B = 128 * (D + 16) * 2;
+    constexpr uint32_t TM_S = 0, TM_PV = 128;
     uint8_t* Qs = sm;
-    uint8_t* Ks = sm + TILE_B;            // [2]
-    uint8_t* Vs = sm + 3 * TILE_B;        // [2]
-    uint8_t* Ps = sm + 5 * TILE_B;        // 128 x 128 bf16
+    uint8_t* Ks = sm + TILE_B;                          // [2]
+    uint8_t* Vs = sm + 3 * TILE_B;                      // [2] x (D+16 columns)
+    uint8_t* Ps = sm + 3 * TILE_B + 2 * VTILE_B;        // 128 x 128 bf16
     const int tid = threadIdx.x, warp = tid >> 5;
     const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 128;
     const int kvh = h / (H / Hkv);
@@ -146,8 +165,9 @@ attn_fwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
     const bf16* Vbase = Vb + ((size_t)(b * Hkv + kvh) * S) * D;
     const int nkv = (S + 127) / 128;
 
-    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 128);
-    if (tid == 0) { tc::mbar_init(&mbar[0], 1); tc::mbar_init(&mbar[1], 1); tc::mbar_fence_init(); }
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 256);
+    if (tid == 0) { tc::mbar_init(&mbar, 1); tc::mbar_fence_init(); }
+    uint4 kreg[D / 8], vreg[D / 8];                     // register-staged K/V rows of a future tile
     {
         uint4 r[D / 8];
         load_row<D>(Qb + ((size_t)(b * H + h) * S + (valid_q ? q : 0)) * D, valid_q, r);
@@ -157,6 +177,17 @@ attn_fwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
         store_row<D>(Ks, tid, r);
         load_row<D>(Vbase + (size_t)(vk ? tid : 0) * D, vk, r);
         store_row<D>(Vs, tid, r);
+#pragma unroll
+        for (int bb = 0; bb < 2; ++bb) {                // constant ones / zero chunks (bf16 1.0 = 0x3F80)
+            *reinterpret_cast<uint4*>(Vs + bb * VTILE_B + (D / 8) * (128 * 16) + tid * 16) = make_uint4(0x00003F80u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(Vs + bb * VTILE_B + (D / 8 + 1) * (128 * 16) + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (nkv > 1) {
+            const int kn = 128 + tid;
+            const bool v1 = kn < S;
+            load_row<D>(Kbase + (size_t)(v1 ? kn : 0) * D, v1, kreg);
+            load_row<D>(Vbase + (size_t)(v1 ? kn : 0) * D, v1, vreg);
+        }
     }
     tc::fence_async_smem();
     tc::fence_before_sync();
@@ -166,92 +197,111 @@ attn_fwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
     const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
     const uint32_t sQ = tc::smem_u32(Qs), sP = tc::smem_u32(Ps);
     constexpr uint32_t idescS = tc::make_idesc_bf16(128, 128, 0, 0);
-    constexpr uint32_t idescPV = tc::make_idesc_bf16(128, D, 0, 1);
+    constexpr uint32_t idescPV = tc::make_idesc_bf16(128, D + 16, 0, 1);
+    const tc::Desc dQ_ = tc::kmajor(sQ, 128), dP_ = tc::kmajor(sP, 128);
+    const tc::Desc dK0 = tc::kmajor(tc::smem_u32(Ks), 128), dK1 = tc::kmajor(tc::smem_u32(Ks + TILE_B), 128);
+    const tc::Desc dV0 = tc::mnmajor(tc::smem_u32(Vs), 128), dV1 = tc::mnmajor(tc::smem_u32(Vs + VTILE_B), 128);
+    constexpr uint32_t KS = tc::kstep_kmajor(128);
+    if (warp == 0) {
+        if (tc::elect_one()) {
+#pragma unroll
+            for (int s = 0; s < D / 16; ++s)
+                tc::mma_bf16(tmem + TM_S, dQ_.adv(s * KS).u64(), dK0.adv(s * KS).u64(), idescS, s > 0);
+            tc::mma_commit(&mbar);
+        }
+        __syncwarp();
+    }
 
-    float m = -INFINITY, l = 0.f;
+    float m = -INFINITY, l = 0.f, alpha_prev = 0.f;     // m in the scaled log2 domain
     float O[D];
 #pragma unroll
     for (int c = 0; c < D; ++c) O[c] = 0.f;
-    uint32_t ph0 = 0, ph1 = 0;
+    uint32_t ph = 0;
 
-    for (int j = 0; j < nkv; ++j) {
-        const int buf = j & 1;
-        const uint32_t sK = tc::smem_u32(Ks + buf * TILE_B), sV = tc::smem_u32(Vs + buf * TILE_B);
-        if (tid == 0) {
+    for (int j = 0; j <= nkv; ++j) {
+        tc::mbar_wait(&mbar, ph); ph ^= 1;              // S_j (j < nkv) and P_{j-1} V_{j-1} (j > 0) are complete
+        tc::fence_after_sync();
+        if (j > 0) {                                    // deferred O / l update with tile j-1
 #pragma unroll
-            for (int s = 0; s < D / 16; ++s)
-                tc::mma_bf16(tmem, tc::desc_kmajor(sQ, 128, s), tc::desc_kmajor(sK, 128, s), idescS, s > 0);
-            tc::mma_commit(&mbar[0]);
+            for (int c0 = 0; c0 < D; c0 += 32) {
+                float t[32];
+                tc::tmem_ld32(tlane + TM_PV + c0, t);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) O[c0 + c] = fmaf(O[c0 + c], alpha_prev, t[c]);
+            }
+            float t[16];
+            tc::tmem_ld16(tlane + TM_PV + D, t);
+            l = fmaf(l, alpha_prev, t[0]);
         }
-        // prefetch the next K/V rows into registers while the tensor core works
-        uint4 kreg[D / 8], vreg[D / 8];
-        const bool have_next = j + 1 < nkv;
-        if (have_next) {
-            const int kn = (j + 1) * 128 + tid;
+        if (j == nkv) break;
+        const int buf = j & 1;
+        if (j + 1 < nkv) {                              // K/V of tile j+1 -> the other buffer (its readers finished)
+            store_row<D>(Ks + (buf ^ 1) * TILE_B, tid, kreg);
+            store_row<D>(Vs + (buf ^ 1) * VTILE_B, tid, vreg);
+        }
+        if (j + 2 < nkv) {                              // start fetching tile j+2
+            const int kn = (j + 2) * 128 + tid;
             const bool vk = kn < S;
             load_row<D>(Kbase + (size_t)(vk ? kn : 0) * D, vk, kreg);
             load_row<D>(Vbase + (size_t)(vk ? kn : 0) * D, vk, vreg);
         }
-        tc::mbar_wait(&mbar[0], ph0); ph0 ^= 1;
-        tc::fence_after_sync();
-
         float sv[128];
+        {
+            uint32_t r0[32], r1[32], r2[32], r3[32];
+            tc::tmem_ld32_nowait(tlane + TM_S, r0);
+            tc::tmem_ld32_nowait(tlane + TM_S + 32, r1);
+            tc::tmem_ld32_nowait(tlane + TM_S + 64, r2);
+            tc::tmem_ld32_nowait(tlane + TM_S + 96, r3);
+            tc::tmem_wait_ld();
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-            float t[32];
-            tc::tmem_ld32(tlane + c4 * 32, t);
-#pragma unroll
-            for (int c = 0; c < 32; ++c) sv[c4 * 32 + c] = t[c] * scale_log2;
+            for (int c = 0; c < 32; ++c) {
+                sv[c] = __uint_as_float(r0[c]); sv[32 + c] = __uint_as_float(r1[c]);
+                sv[64 + c] = __uint_as_float(r2[c]); sv[96 + c] = __uint_as_float(r3[c]);
+            }
         }
-        const int kvalid = S - j * 128;            // keys >= kvalid in this tile are padding
+        const int kvalid = S - j * 128;                 // keys >= kvalid in this tile are padding
         if (kvalid < 128) {
 #pragma unroll
             for (int c = 0; c < 128; ++c) if (c >= kvalid) sv[c] = -INFINITY;
         }
-        float mx = m;
+        float mr = fmax3(sv[0], sv[1], sv[2]);
 #pragma unroll
-        for (int c = 0; c < 128; ++c) mx = fmaxf(mx, sv[c]);
-        const float alpha = exp2f(m - mx);          // m = -inf on the first tile -> 0
-        float rs = 0.f;
+        for (int c = 3; c + 1 < 128; c += 2) mr = fmax3(mr, sv[c], sv[c + 1]);
+        mr = fmaxf(mr, sv[127]);
+        const float mx = fmaxf(m, mr * scale_log2);
+        alpha_prev = ex2_approx(m - mx);                // m = -inf on the first tile -> 0
+        const float nmx = -mx;
 #pragma unroll
         for (int c8 = 0; c8 < 16; ++c8) {
             float p[8];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) { p[c] = exp2f(sv[c8 * 8 + c] - mx); rs += p[c]; }
+            for (int c = 0; c < 8; ++c) p[c] = ex2_approx(fmaf(sv[c8 * 8 + c], scale_log2, nmx));
             uint4 o;
             o.x = tc::pack_bf16(p[0], p[1]); o.y = tc::pack_bf16(p[2], p[3]);
             o.z = tc::pack_bf16(p[4], p[5]); o.w = tc::pack_bf16(p[6], p[7]);
             *reinterpret_cast<uint4*>(Ps + c8 * (128 * 16) + tid * 16) = o;
         }
-        l = l * alpha + rs;
         m = mx;
         tc::fence_async_smem();
         tc::fence_before_sync();
         __syncthreads();
-        if (tid == 0) {
-            tc::fence_after_sync();
+        if (warp == 0) {
+            if (tc::elect_one()) {
+                tc::fence_after_sync();
+                const tc::Desc dV = buf ? dV1 : dV0;
 #pragma unroll
-            for (int s = 0; s < 8; ++s)
-                tc::mma_bf16(tmem, tc::desc_kmajor(sP, 128, s), tc::desc_mnmajor(sV, 128, s), idescPV, s > 0);
-            tc::mma_commit(&mbar[1]);
-        }
-        if (have_next) {
-            store_row<D>(Ks + (buf ^ 1) * TILE_B, tid, kreg);
-            store_row<D>(Vs + (buf ^ 1) * TILE_B, tid, vreg);
-        }
-        tc::mbar_wait(&mbar[1], ph1); ph1 ^= 1;
-        tc::fence_after_sync();
+                for (int s = 0; s < 8; ++s)
+                    tc::mma_bf16(tmem + TM_PV, dP_.adv(s * KS).u64(), dV.adv(s * tc::KSTEP_MN).u64(), idescPV, s > 0);
+                if (j + 1 < nkv) {
+                    const tc::Desc dK = buf ? dK0 : dK1;
 #pragma unroll
-        for (int c0 = 0; c0 < D; c0 += 32) {
-            float t[32];
-            tc::tmem_ld32(tlane + c0, t);
-#pragma unroll
-            for (int c = 0; c < 32; ++c) O[c0 + c] = O[c0 + c] * alpha + t[c];
+                    for (int s = 0; s < D / 16; ++s)
+                        tc::mma_bf16(tmem + TM_S, dQ_.adv(s * KS).u64(), dK.adv(s * KS).u64(), idescS, s > 0);
+                }
+                tc::mma_commit(&mbar);
+            }
+            __syncwarp();
         }
-        tc::fence_async_smem();
-        tc::fence_before_sync();
-        __syncthreads();
-        tc::fence_after_sync();
     }
     if (valid_q) {
         const float inv = 1.0f / l;
@@ -261,28 +311,37 @@ attn_fwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
             *reinterpret_cast<float4*>(o + c) = make_float4(O[c] * inv, O[c + 1] * inv, O[c + 2] * inv, O[c + 3] * inv);
         lse[((size_t)b * H + h) * S + q] = m + log2f(l);
     }
+    tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, 128);
+    if (warp == 0) tc::tmem_dealloc(tmem, 256);
 }
 
 // --------------------------------------------------------------------------- backward
+// CTA = 128 keys of one (batch, head), 256 threads, loop over 128-query tiles processed as two
+// 64-query halves so that the TMEM footprint (S^T 64 + dP^T 64 + dV + dK + dQ columns) fits 256
+// columns and TWO CTAs share an SM.  Software pipeline: one mbarrier wait + one CTA barrier per half;
+// after the exp/FMA phase of a half the issuing thread queues dV, dK (and dQ on the second half) of
+// THIS half and S^T, dP^T of the NEXT half back to back; Q / dO tiles are double buffered in shared
+// memory and staged through registers one tile ahead.
 template <int D>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, 2)
 attn_bwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const bf16* __restrict__ Vb,
                 const bf16* __restrict__ dOb, const float* __restrict__ lse, const float* __restrict__ Dvec,
                 float* __restrict__ dQacc, float* __restrict__ dKh, float* __restrict__ dVh,
-                int S, int H, int Hkv, float scale, float scale_log2) {
+                int S, int H, int Hkv, float scale, float scale_log2, int debug) {
     extern __shared__ __align__(1024) uint8_t sm[];
-    __shared__ uint64_t mbar[2];
+    __shared__ uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
-    __shared__ float lse_s[128], D_s[128];
+    __shared__ __align__(16) float nlse_s[2][128];    // -lse (log2 domain); -inf for padding queries
+    __shared__ __align__(16) float D_s[2][128];
     constexpr int TILE_B = 128 * D * 2;
+    constexpr uint32_t TM_COLS = (128 + 3 * D <= 256) ? 256 : 512;
     uint8_t* Kt = sm;
     uint8_t* Vt = sm + TILE_B;
-    uint8_t* Qs = sm + 2 * TILE_B;
-    uint8_t* dOs = sm + 3 * TILE_B;
-    uint8_t* PTs = sm + 4 * TILE_B;                 // P^T  [128 keys x 128 q] bf16
-    uint8_t* dSs = PTs + 128 * 128 * 2;             // dS^T [128 keys x 128 q] bf16
+    uint8_t* Qs = sm + 2 * TILE_B;                  // [2]
+    uint8_t* dOs = sm + 4 * TILE_B;                 // [2]
+    uint8_t* PTs = sm + 6 * TILE_B;                 // P^T of the current half  [128 keys x 64 q] bf16
+    uint8_t* dSs = PTs + 128 * 64 * 2;              // dS^T of the whole tile   [128 keys x 128 q] bf16
     const int tid = threadIdx.x, warp = tid >> 5;
     const int row = tid & 127, half = tid >> 7;
     const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * 128;
@@ -290,16 +349,32 @@ attn_bwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
     const int key = k0 + row;
     const bool valid_k = key < S;
     const size_t head_off = ((size_t)(b * H + h) * S) * D;
+    const size_t stat_off = ((size_t)b * H + h) * S;
     const int nq = (S + 127) / 128;
-    constexpr uint32_t TM_ST = 0, TM_DPT = 128, TM_DV = 256, TM_DK = 256 + D, TM_DQ = 256 + 2 * D;
+    constexpr uint32_t TM_ST = 0, TM_DPT = 64, TM_DV = 128, TM_DK = 128 + D, TM_DQ = 128 + 2 * D;
+    const bf16* tile_src = (half == 0 ? Qb : dOb) + head_off;
+    const float* stat_src = (half == 0 ? lse : Dvec) + stat_off;
 
-    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
-    if (tid == 0) { tc::mbar_init(&mbar[0], 1); tc::mbar_init(&mbar[1], 1); tc::mbar_fence_init(); }
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, TM_COLS);
+    if (tid == 0) { tc::mbar_init(&mbar, 1); tc::mbar_fence_init(); }
+    uint4 nreg[D / 8];
+    float nstat = 0.f;
     {
         uint4 r[D / 8];
         const bf16* base = (half == 0 ? Kb : Vb) + ((size_t)(b * Hkv + kvh) * S + (valid_k ? key : 0)) * D;
         load_row<D>(base, valid_k, r);
         store_row<D>(half == 0 ? Kt : Vt, row, r);
+        const bool vq = row < S;                     // query tile 0 -> buffer 0
+        load_row<D>(tile_src + (size_t)(vq ? row : 0) * D, vq, r);
+        store_row<D>(half == 0 ? Qs : dOs, row, r);
+        const float st0 = vq ? stat_src[row] : (half == 0 ? INFINITY : 0.f);
+        if (half == 0) nlse_s[0][row] = -st0; else D_s[0][row] = st0;
+        if (nq > 1) {                                // tile 1 -> registers
+            const int qn = 128 + row;
+            const bool v1 = qn < S;
+            load_row<D>(tile_src + (size_t)(v1 ? qn : 0) * D, v1, nreg);
+            nstat = v1 ? stat_src[qn] : (half == 0 ? INFINITY : 0.f);
+        }
     }
     tc::fence_async_smem();
     tc::fence_before_sync();
@@ -307,129 +382,180 @@ attn_bwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
     tc::fence_after_sync();
     const uint32_t tmem = tmem_base_s;
     const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const uint32_t sK = tc::smem_u32(Kt), sV = tc::smem_u32(Vt), sQ = tc::smem_u32(Qs), sdO = tc::smem_u32(dOs);
+    const uint32_t sK = tc::smem_u32(Kt), sV = tc::smem_u32(Vt), sQ0 = tc::smem_u32(Qs), sdO0 = tc::smem_u32(dOs);
     const uint32_t sPT = tc::smem_u32(PTs), sdS = tc::smem_u32(dSs);
-    constexpr uint32_t idesc128 = tc::make_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t idesc64 = tc::make_idesc_bf16(128, 64, 0, 0);
     constexpr uint32_t idescKM = tc::make_idesc_bf16(128, D, 0, 1);     // A K-major, B MN-major
     constexpr uint32_t idescMM = tc::make_idesc_bf16(128, D, 1, 1);     // A MN-major, B MN-major
-    uint32_t ph0 = 0, ph1 = 0;
+    uint32_t ph = 0;
+
+    constexpr uint32_t KS = tc::kstep_kmajor(128);
+    const tc::Desc kK = tc::kmajor(sK, 128), kV = tc::kmajor(sV, 128), mK = tc::mnmajor(sK, 128);
+    const tc::Desc kPT = tc::kmajor(sPT, 128), kdS = tc::kmajor(sdS, 128), mdS = tc::mnmajor(sdS, 128);
+    const tc::Desc kQ = tc::kmajor(sQ0, 128), kdO = tc::kmajor(sdO0, 128), mQ = tc::mnmajor(sQ0, 128), mdO = tc::mnmajor(sdO0, 128);
+    // queues S^T and dP^T of (tile buffer `bq`, half `hq`)
+    auto issue_scores = [&](int bq, int hq) {
+        const uint32_t off = bq * TILE_B + hq * 64 * 16;
+#pragma unroll
+        for (int s = 0; s < D / 16; ++s)
+            tc::mma_bf16(tmem + TM_ST, kK.adv(s * KS).u64(), kQ.adv(off + s * KS).u64(), idesc64, s > 0);
+#pragma unroll
+        for (int s = 0; s < D / 16; ++s)
+            tc::mma_bf16(tmem + TM_DPT, kV.adv(s * KS).u64(), kdO.adv(off + s * KS).u64(), idesc64, s > 0);
+    };
+    // dQ of the previous tile (rows = queries) -> global accumulation.  Each warp transposes its
+    // 32-row x D/2-column block through a private shared slice so that every vector reduction
+    // covers fully used 32-byte sectors (a thread's own row would touch half a sector per request).
+    // The staging bytes are carved from the part of the P^T tile that only this warp writes in its
+    // next exp phase (chunks half*4 .. half*4+3, rows 32*(warp&3) ..): 4 pieces of 8 rows x 64 B.
+    const int lane = tid & 31;
+    uint8_t* xbase = PTs + (half * 4) * (128 * 16) + ((warp & 3) * 32) * 16;
+    auto xaddr = [&](int r, int c) -> float* {       // r: row 0..31 of the warp block, c: float column 0..15
+        return reinterpret_cast<float*>(xbase + (r >> 3) * (128 * 16) + (r & 7) * 64) + c;
+    };
+    auto dq_epilogue = [&](int q0) {
+        if constexpr (D != 32) {                      // wide heads: one row per thread (1 CTA/SM path anyway)
+            const int qq = q0 + row;
+            float t[32];
+            tc::tmem_ld32(tlane + TM_DQ + half * 32, t);
+            if (qq < S && !(debug & 1)) {
+#pragma unroll
+                for (int c = 0; c < 32; c += 4)
+                    atomicAdd(reinterpret_cast<float4*>(dQacc + head_off + (size_t)qq * D + half * 32 + c),
+                              make_float4(t[c] * scale, t[c + 1] * scale, t[c + 2] * scale, t[c + 3] * scale));
+            }
+            return;
+        }
+        float t[16];
+        tc::tmem_ld16(tlane + TM_DQ + half * 16, t);
+#pragma unroll
+        for (int c = 0; c < 16; c += 4)
+            *reinterpret_cast<float4*>(xaddr(lane, c)) = make_float4(t[c] * scale, t[c + 1] * scale, t[c + 2] * scale, t[c + 3] * scale);
+        __syncwarp();
+        if (!(debug & 1)) {
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {          // 8 rows x 64 B per warp instruction
+                const int r = it * 8 + (lane >> 2), ch = lane & 3;
+                const int qq = q0 + (warp & 3) * 32 + r;
+                if (qq < S) {
+                    const float4 v = *reinterpret_cast<const float4*>(xaddr(r, ch * 4));
+                    atomicAdd(reinterpret_cast<float4*>(dQacc + head_off + (size_t)qq * D + half * 16 + ch * 4), v);
+                }
+            }
+        }
+        __syncwarp();
+    };
+
+    if (warp == 0) {
+        if (tc::elect_one()) { issue_scores(0, 0); tc::mma_commit(&mbar); }
+        __syncwarp();
+    }
 
     for (int i = 0; i < nq; ++i) {
-        const int q0 = i * 128;
-        {
-            const int qq = q0 + row;
-            const bool vq = qq < S;
-            uint4 r[D / 8];
-            load_row<D>((half == 0 ? Qb : dOb) + head_off + (size_t)(vq ? qq : 0) * D, vq, r);
-            store_row<D>(half == 0 ? Qs : dOs, row, r);
-            if (half == 0) lse_s[row] = vq ? lse[((size_t)b * H + h) * S + qq] : INFINITY;
-            else D_s[row] = vq ? Dvec[((size_t)b * H + h) * S + qq] : 0.f;
-        }
-        tc::fence_async_smem();
-        tc::fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {
+        const int bq = i & 1;
+#pragma unroll
+        for (int hq = 0; hq < 2; ++hq) {
+            tc::mbar_wait(&mbar, ph); ph ^= 1;        // scores of (i, hq) ready; every earlier MMA has completed
             tc::fence_after_sync();
+            if (hq == 0 && i > 0) dq_epilogue((i - 1) * 128);
+            {
+                const int c0 = half * 32;             // this thread's 32 query columns of the half
+                float st[32], dp[32];
+                {
+                    uint32_t r0[32], r1[32];
+                    tc::tmem_ld32_nowait(tlane + TM_ST + c0, r0);
+                    tc::tmem_ld32_nowait(tlane + TM_DPT + c0, r1);
+                    tc::tmem_wait_ld();
 #pragma unroll
-            for (int s = 0; s < D / 16; ++s)
-                tc::mma_bf16(tmem + TM_ST, tc::desc_kmajor(sK, 128, s), tc::desc_kmajor(sQ, 128, s), idesc128, s > 0);
-#pragma unroll
-            for (int s = 0; s < D / 16; ++s)
-                tc::mma_bf16(tmem + TM_DPT, tc::desc_kmajor(sV, 128, s), tc::desc_kmajor(sdO, 128, s), idesc128, s > 0);
-            tc::mma_commit(&mbar[0]);
-        }
-        tc::mbar_wait(&mbar[0], ph0); ph0 ^= 1;
-        tc::fence_after_sync();
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-            const int c0 = half * 64 + cc * 32;
-            float st[32], dp[32];
-            tc::tmem_ld32(tlane + TM_ST + c0, st);
-            tc::tmem_ld32(tlane + TM_DPT + c0, dp);
-#pragma unroll
-            for (int c8 = 0; c8 < 4; ++c8) {
-                float p[8], ds[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const int qc = c0 + c8 * 8 + c;
-                    const float pv = valid_k ? exp2f(st[c8 * 8 + c] * scale_log2 - lse_s[qc]) : 0.f;
-                    p[c] = pv;
-                    ds[c] = pv * (dp[c8 * 8 + c] - D_s[qc]) * scale;
+                    for (int c = 0; c < 32; ++c) { st[c] = __uint_as_float(r0[c]); dp[c] = __uint_as_float(r1[c]); }
                 }
-                uint4 o;
-                o.x = tc::pack_bf16(p[0], p[1]); o.y = tc::pack_bf16(p[2], p[3]);
-                o.z = tc::pack_bf16(p[4], p[5]); o.w = tc::pack_bf16(p[6], p[7]);
-                const int chunk = (c0 >> 3) + c8;
-                *reinterpret_cast<uint4*>(PTs + chunk * (128 * 16) + row * 16) = o;
-                o.x = tc::pack_bf16(ds[0], ds[1]); o.y = tc::pack_bf16(ds[2], ds[3]);
-                o.z = tc::pack_bf16(ds[4], ds[5]); o.w = tc::pack_bf16(ds[6], ds[7]);
-                *reinterpret_cast<uint4*>(dSs + chunk * (128 * 16) + row * 16) = o;
-            }
-        }
-        tc::fence_async_smem();
-        tc::fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {
-            tc::fence_after_sync();
+                if (!valid_k) {                       // padding keys: exp2(-inf) = 0 -> P = dS = 0
 #pragma unroll
-            for (int s = 0; s < 8; ++s)   // dV[key,d] += P^T[key,q] dO[q,d]
-                tc::mma_bf16(tmem + TM_DV, tc::desc_kmajor(sPT, 128, s), tc::desc_mnmajor(sdO, 128, s), idescKM, (i > 0) || (s > 0));
-#pragma unroll
-            for (int s = 0; s < 8; ++s)   // dK[key,d] += dS^T[key,q] Q[q,d]
-                tc::mma_bf16(tmem + TM_DK, tc::desc_kmajor(sdS, 128, s), tc::desc_mnmajor(sQ, 128, s), idescKM, (i > 0) || (s > 0));
-#pragma unroll
-            for (int s = 0; s < 8; ++s)   // dQ[q,d] = dS[q,key] K[key,d]
-                tc::mma_bf16(tmem + TM_DQ, tc::desc_mnmajor(sdS, 128, s), tc::desc_mnmajor(sK, 128, s), idescMM, s > 0);
-            tc::mma_commit(&mbar[1]);
-        }
-        tc::mbar_wait(&mbar[1], ph1); ph1 ^= 1;
-        tc::fence_after_sync();
-        {
-            const int qq = q0 + row;                 // dQ rows are queries
-            float* dst = dQacc + head_off + (size_t)qq * D + half * (D / 2);
-            if constexpr (D == 32) {
-                float t[16];
-                tc::tmem_ld16(tlane + TM_DQ + half * 16, t);
-                if (qq < S) {
-#pragma unroll
-                    for (int c = 0; c < 16; c += 4)
-                        atomicAdd(reinterpret_cast<float4*>(dst + c), make_float4(t[c], t[c + 1], t[c + 2], t[c + 3]));
+                    for (int c = 0; c < 32; ++c) st[c] = -INFINITY;
                 }
-            } else {
-                float t[32];
-                tc::tmem_ld32(tlane + TM_DQ + half * 32, t);
-                if (qq < S) {
+                const float* nl_p = &nlse_s[bq][hq * 64 + c0];
+                const float* dd_p = &D_s[bq][hq * 64 + c0];
 #pragma unroll
-                    for (int c = 0; c < 32; c += 4)
-                        atomicAdd(reinterpret_cast<float4*>(dst + c), make_float4(t[c], t[c + 1], t[c + 2], t[c + 3]));
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    const float4 l0 = *reinterpret_cast<const float4*>(nl_p + c8 * 8);
+                    const float4 l1 = *reinterpret_cast<const float4*>(nl_p + c8 * 8 + 4);
+                    const float4 d0 = *reinterpret_cast<const float4*>(dd_p + c8 * 8);
+                    const float4 d1 = *reinterpret_cast<const float4*>(dd_p + c8 * 8 + 4);
+                    const float nl[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+                    const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+                    float p[8], ds[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        p[c] = ex2_approx(fmaf(st[c8 * 8 + c], scale_log2, nl[c]));
+                        ds[c] = p[c] * (dp[c8 * 8 + c] - dd[c]);          // unscaled; `scale` is applied to dQ / dK at the end
+                    }
+                    uint4 o;
+                    o.x = tc::pack_bf16(p[0], p[1]); o.y = tc::pack_bf16(p[2], p[3]);
+                    o.z = tc::pack_bf16(p[4], p[5]); o.w = tc::pack_bf16(p[6], p[7]);
+                    *reinterpret_cast<uint4*>(PTs + (half * 4 + c8) * (128 * 16) + row * 16) = o;
+                    o.x = tc::pack_bf16(ds[0], ds[1]); o.y = tc::pack_bf16(ds[2], ds[3]);
+                    o.z = tc::pack_bf16(ds[4], ds[5]); o.w = tc::pack_bf16(ds[6], ds[7]);
+                    *reinterpret_cast<uint4*>(dSs + (hq * 8 + half * 4 + c8) * (128 * 16) + row * 16) = o;
                 }
             }
+            if (hq == 0 && i + 1 < nq) {              // tile i+1: registers -> the other buffer; fetch tile i+2
+                store_row<D>((half == 0 ? Qs : dOs) + (bq ^ 1) * TILE_B, row, nreg);
+                if (half == 0) nlse_s[bq ^ 1][row] = -nstat; else D_s[bq ^ 1][row] = nstat;
+                if (i + 2 < nq) {
+                    const int qn = (i + 2) * 128 + row;
+                    const bool vq = qn < S;
+                    load_row<D>(tile_src + (size_t)(vq ? qn : 0) * D, vq, nreg);
+                    nstat = vq ? stat_src[qn] : (half == 0 ? INFINITY : 0.f);
+                }
+            }
+            tc::fence_async_smem();
+            tc::fence_before_sync();
+            __syncthreads();
+            if (warp == 0) {
+                if (tc::elect_one()) {
+                    tc::fence_after_sync();
+                    const uint32_t off = bq * TILE_B + hq * 64 * 16;
+#pragma unroll
+                    for (int s = 0; s < 4; ++s)   // dV[key,d] += P^T[key, 64 q] dO[64 q, d]
+                        tc::mma_bf16(tmem + TM_DV, kPT.adv(s * KS).u64(), mdO.adv(off + s * tc::KSTEP_MN).u64(), idescKM,
+                                     (i > 0) || (hq > 0) || (s > 0));
+#pragma unroll
+                    for (int s = 0; s < 4; ++s)   // dK[key,d] += dS^T[key, 64 q] Q[64 q, d]
+                        tc::mma_bf16(tmem + TM_DK, kdS.adv((hq * 4 + s) * KS).u64(), mQ.adv(off + s * tc::KSTEP_MN).u64(), idescKM,
+                                     (i > 0) || (hq > 0) || (s > 0));
+                    if (hq == 1) {
+#pragma unroll
+                        for (int s = 0; s < 8; ++s)   // dQ[q,d] = dS[q, key] K[key, d] over all 128 queries of the tile
+                            tc::mma_bf16(tmem + TM_DQ, mdS.adv(s * tc::KSTEP_MN).u64(), mK.adv(s * tc::KSTEP_MN).u64(), idescMM, s > 0);
+                    }
+                    if (hq == 0) issue_scores(bq, 1);
+                    else if (i + 1 < nq) issue_scores(bq ^ 1, 0);
+                    tc::mma_commit(&mbar);
+                }
+                __syncwarp();
+            }
         }
-        tc::fence_before_sync();
-        __syncthreads();
-        tc::fence_after_sync();
     }
-    // ---- epilogue: dK, dV of this key tile ----
+    tc::mbar_wait(&mbar, ph); ph ^= 1;
+    tc::fence_after_sync();
+    dq_epilogue((nq - 1) * 128);
+    // ---- epilogue: dK (scaled), dV of this key tile ----
     {
         float* dk = dKh + head_off + (size_t)key * D + half * (D / 2);
         float* dv = dVh + head_off + (size_t)key * D + half * (D / 2);
-        if constexpr (D == 32) {
-            float t[16];
-            tc::tmem_ld16(tlane + TM_DK + half * 16, t);
-            if (valid_k) for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(dk + c) = make_float4(t[c], t[c + 1], t[c + 2], t[c + 3]);
-            tc::tmem_ld16(tlane + TM_DV + half * 16, t);
-            if (valid_k) for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(dv + c) = make_float4(t[c], t[c + 1], t[c + 2], t[c + 3]);
-        } else {
-            float t[32];
-            tc::tmem_ld32(tlane + TM_DK + half * 32, t);
-            if (valid_k) for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(dk + c) = make_float4(t[c], t[c + 1], t[c + 2], t[c + 3]);
-            tc::tmem_ld32(tlane + TM_DV + half * 32, t);
-            if (valid_k) for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(dv + c) = make_float4(t[c], t[c + 1], t[c + 2], t[c + 3]);
-        }
+        float t[D / 2];
+        if constexpr (D == 32) tc::tmem_ld16(tlane + TM_DK + half * 16, t);
+        else tc::tmem_ld32(tlane + TM_DK + half * 32, t);
+        if (valid_k) for (int c = 0; c < D / 2; c += 4)
+            *reinterpret_cast<float4*>(dk + c) = make_float4(t[c] * scale, t[c + 1] * scale, t[c + 2] * scale, t[c + 3] * scale);
+        if constexpr (D == 32) tc::tmem_ld16(tlane + TM_DV + half * 16, t);
+        else tc::tmem_ld32(tlane + TM_DV + half * 32, t);
+        if (valid_k) for (int c = 0; c < D / 2; c += 4)
+            *reinterpret_cast<float4*>(dv + c) = make_float4(t[c], t[c + 1], t[c + 2], t[c + 3]);
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+    if (warp == 0) tc::tmem_dealloc(tmem, TM_COLS);
 }
 
 // --------------------------------------------------------------------------- host side
@@ -492,11 +618,11 @@ int gaot_attn_forward(const float* q, const float* k, const float* v, int64_t B,
     dim3 grid((unsigned)((S + 127) / 128), (unsigned)H, (unsigned)B);
     GAOT_TIME_KERNEL("attn_fwd", st, 4.0 * (double)B * H * (double)S * (double)S * d);
     if (d == 32) {
-        const size_t smem = 5 * 128 * 32 * 2 + 128 * 128 * 2;
+        const size_t smem = 3 * 128 * 32 * 2 + 2 * 128 * 48 * 2 + 128 * 128 * 2;
         GAOT_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attn_fwd_kernel<32><<<grid, 128, smem, st>>>(w.Qb, w.Kb, w.Vb, out, lse, (int)S, H, Hkv, scale_log2);
     } else {
-        const size_t smem = 5 * 128 * 64 * 2 + 128 * 128 * 2;
+        const size_t smem = 3 * 128 * 64 * 2 + 2 * 128 * 80 * 2 + 128 * 128 * 2;
         GAOT_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attn_fwd_kernel<64><<<grid, 128, smem, st>>>(w.Qb, w.Kb, w.Vb, out, lse, (int)S, H, Hkv, scale_log2);
     }
@@ -519,19 +645,21 @@ int gaot_attn_backward(const float* q, const float* k, const float* v, const flo
     GAOT_LAUNCH_CHECK();
     GAOT_CUDA(cudaMemsetAsync(w.dQacc, 0, (size_t)B * H * S * d * sizeof(float), st));
     const float scale = 1.0f / sqrtf((float)d), scale_log2 = scale * 1.4426950408889634f;
+    const char* dbg_env = getenv("GAOT_ATTN_DEBUG");
+    const int dbg = dbg_env ? atoi(dbg_env) : 0;
     dim3 grid((unsigned)((S + 127) / 128), (unsigned)H, (unsigned)B);
     {
     GAOT_TIME_KERNEL("attn_bwd", st, 10.0 * (double)B * H * (double)S * (double)S * d);
     if (d == 32) {
-        const size_t smem = 4 * 128 * 32 * 2 + 2 * 128 * 128 * 2;
+        const size_t smem = 6 * 128 * 32 * 2 + 128 * 64 * 2 + 128 * 128 * 2;
         GAOT_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attn_bwd_kernel<32><<<grid, 256, smem, st>>>(w.Qb, w.Kb, w.Vb, w.dOb, lse, w.Dvec, w.dQacc, w.dKh, w.dVh,
-                                                     (int)S, H, Hkv, scale, scale_log2);
+                                                     (int)S, H, Hkv, scale, scale_log2, dbg);
     } else {
-        const size_t smem = 4 * 128 * 64 * 2 + 2 * 128 * 128 * 2;
+        const size_t smem = 6 * 128 * 64 * 2 + 128 * 64 * 2 + 128 * 128 * 2;
         GAOT_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attn_bwd_kernel<64><<<grid, 256, smem, st>>>(w.Qb, w.Kb, w.Vb, w.dOb, lse, w.Dvec, w.dQacc, w.dKh, w.dVh,
-                                                     (int)S, H, Hkv, scale, scale_log2);
+                                                     (int)S, H, Hkv, scale, scale_log2, dbg);
     }
     }
     GAOT_LAUNCH_CHECK();

@@ -35,6 +35,29 @@ __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_saddr, uint32_t r
     return make_desc(tile_saddr + kstep * 256u, 128u, rows * 16u);
 }
 
+// Precomputed descriptor whose start address can be advanced with one 32-bit add (the 14-bit
+// address field never overflows inside the 228 KB shared window).
+struct Desc {
+    uint32_t lo, hi;
+    __device__ __forceinline__ Desc adv(uint32_t bytes) const { return Desc{lo + (bytes >> 4), hi}; }
+    __device__ __forceinline__ uint64_t u64() const { return ((uint64_t)hi << 32) | lo; }
+};
+__device__ __forceinline__ Desc make_desc2(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return Desc{((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16), ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14)};
+}
+// K-major / MN-major views of a chunk-major tile with `rows` rows (see header comment)
+__device__ __forceinline__ Desc kmajor(uint32_t tile_saddr, uint32_t rows) { return make_desc2(tile_saddr, rows * 16u, 128u); }
+__device__ __forceinline__ Desc mnmajor(uint32_t tile_saddr, uint32_t rows) { return make_desc2(tile_saddr, 128u, rows * 16u); }
+// byte advance of one 16-element K step
+__device__ __forceinline__ constexpr uint32_t kstep_kmajor(uint32_t rows) { return 2u * rows * 16u; }
+constexpr uint32_t KSTEP_MN = 256u;
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- instruction descriptor: kind::f16, BF16 x BF16 -> FP32 ----
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
@@ -63,6 +86,20 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+// issue-only variant: the caller batches several loads and then calls tmem_wait_ld() once
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
 }
 
 // ---- TMEM -> registers: 32 lanes x 32 consecutive fp32 columns (thread t <-> lane base+t) ----
