@@ -127,8 +127,10 @@ def sharded_forward(model, batch_local, tokens_pos, n_total: int, group=None, en
     latent = all_reduce_forward(part, group) / cnt.clamp(min=1).unsqueeze(1)
     rn = model.process(latent.view(1, M, -1))
     rn = all_reduce_backward(rn.reshape(M, -1), group)
-    if dec.decoder_strategy == "reverse":
-        dec_edges = _tag(enc_edges.flip(0).contiguous(), False)
+    if dec.decoder_strategy == "reverse":            # flip of the *bidirectional* encoder graph (magno.py:263-273)
+        bi = enc_edges if enc.encoder_strategy == "bidirectional" else \
+            local_encoder_edges("bidirectional", pos, lat, dec.gno_radius, dec.k_neighbors, group)
+        dec_edges = _tag(bi.flip(0).contiguous(), True)
     else:
         from .graph import get_neighbor_strategy
         dec_edges = get_neighbor_strategy(dec.decoder_strategy, pos, None, lat, None, dec.gno_radius, dec.k_neighbors, True)
