@@ -242,6 +242,14 @@ gno_fwd_fixup_kernel(const GnoArgs a, float* __restrict__ out, const float* __re
     }
 }
 
+int gno_fwd_fixup(const GnoArgs& a, float* out, const float* head_partial, cudaStream_t st) {
+    if (a.ntiles > 1) {
+        gno_fwd_fixup_kernel<<<a.ntiles - 1, 64, 0, st>>>(a, out, head_partial);
+        GAOT_LAUNCH_CHECK();
+    }
+    return GAOT_OK;
+}
+
 int gno_forward_fp32(const GnoArgs& a, void* ws, size_t ws_bytes, float* out, cudaStream_t st) {
     const int Cout = a.dims[a.n_layers];
     GAOT_CUDA(cudaMemsetAsync(out, 0, (size_t)a.nq * Cout * sizeof(float), st));

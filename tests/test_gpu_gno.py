@@ -147,3 +147,45 @@ def test_geo_golden_and_oracle():
     close(raw[:, :6], ref[:, :6], rtol=1e-4, atol_rel=1e-5, what="moments")
     close(raw[:, 6:], ref[:, 6:], rtol=1e-3, atol_rel=1e-4, what="eigenvalues")
     assert float(raw[(ref[:, 0] == 0).to(DEV)].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("strategy,dec", [("knn", False), ("radius", True), ("bidirectional", False)])
+def test_gno_bf16_tensor_core_path(strategy, dec):
+    """BF16 tcgen05 MLP path: rtol 2e-2 (north star) against the fp64 oracle; deterministic."""
+    from gaot_3d_b200 import ops
+    torch.manual_seed(1)
+    N, C = 32768, 32
+    phys, lat = synth.surface_cloud(N, seed=2), synth.latent_grid((16, 16, 16))
+    ei = torch.from_numpy(og.get_neighbor_strategy_np(strategy, phys, None, lat, None, 0.15, 2, dec, workers=-1))
+    ypos, xpos = (torch.from_numpy(lat), torch.from_numpy(phys)) if dec else (torch.from_numpy(phys), torch.from_numpy(lat))
+    layers = [6, 64, 64, C] if dec else [6, 64, 64, 64, C]
+    ws = [torch.randn(layers[i + 1], layers[i]) / np.sqrt(layers[i]) for i in range(len(layers) - 1)]
+    bs = [torch.randn(layers[i + 1]) * 0.1 for i in range(len(layers) - 1)]
+    f = torch.randn(ypos.shape[0], C)
+    ref = ogno.integral_transform(ypos.double(), xpos.double(), ei, f.double(), [w.double() for w in ws], [b.double() for b in bs])
+    csr = ops.build_csr(ei[0].to(DEV), ei[1].to(DEV), ypos.shape[0], xpos.shape[0])
+    wd = [w.to(DEV).requires_grad_(True) for w in ws]
+    bd = [b.to(DEV).requires_grad_(True) for b in bs]
+    fd = f.to(DEV).requires_grad_(True)
+    out = ops.gno(ypos.to(DEV), xpos.to(DEV), fd, csr, wd, bd, precision="bf16")
+    o = out.double().cpu()
+    rel_l2 = ((o - ref).norm() / ref.norm()).item()
+    rel_max = ((o - ref).abs().max() / ref.abs().max()).item()
+    assert rel_l2 < 1e-2 and rel_max < 2e-2, (rel_l2, rel_max)
+    assert torch.equal(out, ops.gno(ypos.to(DEV), xpos.to(DEV), fd, csr, wd, bd, precision="bf16"))
+    # spatial sensitivity survives the bf16 operands (hi/lo coordinate split): moving the queries by r/10
+    # must change the output like the oracle says
+    xs = xpos + 0.015
+    ref2 = ogno.integral_transform(ypos.double(), xs.double(), ei, f.double(), [w.double() for w in ws], [b.double() for b in bs])
+    out2 = ops.gno(ypos.to(DEV), xs.to(DEV), fd, csr, wd, bd, precision="bf16").double().cpu()
+    d_ref, d_out = ref2 - ref, out2 - o
+    assert ((d_out - d_ref).norm() / d_ref.norm()).item() < 0.5      # plain bf16 coordinates would give O(1) here
+    # backward (fp32 recompute) still matches the oracle's gradients at the mixed-precision tolerance
+    g = torch.randn_like(ref)
+    wr = [w.double().requires_grad_(True) for w in ws]
+    fr = f.double().requires_grad_(True)
+    ogno.integral_transform(ypos.double(), xpos.double(), ei, fr, wr, [b.double() for b in bs]).backward(g)
+    out.backward(g.float().to(DEV))
+    assert ((fd.grad.double().cpu() - fr.grad).norm() / fr.grad.norm()).item() < 1e-2
+    for i in range(len(ws)):
+        assert ((wd[i].grad.double().cpu() - wr[i].grad).norm() / wr[i].grad.norm()).item() < 1e-2
