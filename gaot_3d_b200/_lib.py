@@ -5,7 +5,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_int, c_int32, c_int64, c_uint64, c_double, c_size_t, c_void_p, c_char_p, POINTER
+from ctypes import c_int, c_int32, c_int64, c_uint64, c_double, c_float, c_size_t, c_void_p, c_char_p, POINTER
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgaot_b200.so")
@@ -47,8 +47,8 @@ _SIGS = {
     "gaot_geo_zscore_workspace_bytes": (c_size_t, [c_int64]),
     "gaot_geo_zscore": (c_int, [P, c_int64, c_int32, P, c_size_t, P]),
     "gaot_attn_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32, c_int32, c_int32]),
-    "gaot_attn_forward": (c_int, [P, P, P, c_int64, c_int64, c_int32, c_int32, c_int32, P, P, c_size_t, P, P, P]),
-    "gaot_attn_backward": (c_int, [P, P, P, P, P, P, c_int64, c_int64, c_int32, c_int32, c_int32, P,
+    "gaot_attn_forward": (c_int, [P, P, P, c_int64, c_int64, c_int32, c_int32, c_int32, P, c_float, c_uint64, P, c_size_t, P, P, P]),
+    "gaot_attn_backward": (c_int, [P, P, P, P, P, P, c_int64, c_int64, c_int32, c_int32, c_int32, P, c_float, c_uint64,
                                    P, c_size_t, P, P, P, P]),
     "gaot_radius_host": (c_int, [P, c_int64, P, c_int64, c_double, c_int, P, P, POINTER(c_int64)]),
     "gaot_knn_host": (c_int, [P, c_int64, P, c_int64, c_int, P, P, POINTER(c_int64)]),

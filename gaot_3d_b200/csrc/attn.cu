@@ -137,15 +137,29 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
     return d;
 }
 
+// Counter-based dropout mask shared by forward and backward (and by oracle/attn.py::dropout_keep):
+// keep(b,h,q,k) = lowbias32(rowkey(b,h,q) ^ k * 0x85EBCA6B) >= thresh, rowkey = lowbias32(seed ^ row * 0x9E3779B1) + seed_hi
+struct DropCfg { uint32_t thresh; uint32_t seed_lo, seed_hi; float inv_keep; };
+__device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ uint32_t drop_rowkey(const DropCfg& dc, uint32_t global_row) {
+    return lowbias32(dc.seed_lo ^ (global_row * 0x9E3779B1u)) + dc.seed_hi;
+}
+__device__ __forceinline__ bool drop_keep(const DropCfg& dc, uint32_t rowkey, uint32_t k) {
+    return lowbias32(rowkey ^ (k * 0x85EBCA6Bu)) >= dc.thresh;
+}
+
 // V tiles carry 16 extra columns: column D is all ones, so the P*V tensor-core product also
 // returns the row sum of the (bf16-rounded) probabilities -- no per-element FADD in the softmax.
 // Software pipeline (one mbarrier wait + one CTA barrier per key tile): after the softmax of tile j
 // the issuing thread queues P_j*V_j AND S_{j+1} = Q K_{j+1}^T back to back; the O update with the
 // P_{j-1}*V_{j-1} result is deferred to the top of the next iteration.
-template <int D>
+template <int D, bool DROP>
 __global__ void __launch_bounds__(128, 2)
 attn_fwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const bf16* __restrict__ Vb,
-                float* __restrict__ out, float* __restrict__ lse, int S, int H, int Hkv, float scale_log2) {
+                float* __restrict__ out, float* __restrict__ lse, int S, int H, int Hkv, float scale_log2, const DropCfg dc) {
     extern __shared__ __align__(1024) uint8_t sm[];
     __shared__ uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
@@ -213,6 +227,8 @@ attn_fwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
     }
 
     float m = -INFINITY, l = 0.f, alpha_prev = 0.f;     // m in the scaled log2 domain
+    float rs_prev = 0.f;                                // DROP: row sum of the un-dropped probabilities of the previous tile
+    const uint32_t rowkey = DROP ? drop_rowkey(dc, (uint32_t)((b * H + h) * S + q)) : 0u;
     float O[D];
 #pragma unroll
     for (int c = 0; c < D; ++c) O[c] = 0.f;
@@ -229,9 +245,13 @@ attn_fwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
 #pragma unroll
                 for (int c = 0; c < 32; ++c) O[c0 + c] = fmaf(O[c0 + c], alpha_prev, t[c]);
             }
-            float t[16];
-            tc::tmem_ld16(tlane + TM_PV + D, t);
-            l = fmaf(l, alpha_prev, t[0]);
+            if (DROP) {
+                l = fmaf(l, alpha_prev, rs_prev);
+            } else {
+                float t[16];
+                tc::tmem_ld16(tlane + TM_PV + D, t);
+                l = fmaf(l, alpha_prev, t[0]);
+            }
         }
         if (j == nkv) break;
         const int buf = j & 1;
@@ -271,17 +291,25 @@ attn_fwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
         const float mx = fmaxf(m, mr * scale_log2);
         alpha_prev = ex2_approx(m - mx);                // m = -inf on the first tile -> 0
         const float nmx = -mx;
+        float rs = 0.f;
 #pragma unroll
         for (int c8 = 0; c8 < 16; ++c8) {
             float p[8];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) p[c] = ex2_approx(fmaf(sv[c8 * 8 + c], scale_log2, nmx));
+            for (int c = 0; c < 8; ++c) {
+                p[c] = ex2_approx(fmaf(sv[c8 * 8 + c], scale_log2, nmx));
+                if (DROP) {
+                    rs += p[c];
+                    p[c] = drop_keep(dc, rowkey, (uint32_t)(j * 128 + c8 * 8 + c)) ? p[c] * dc.inv_keep : 0.f;
+                }
+            }
             uint4 o;
             o.x = tc::pack_bf16(p[0], p[1]); o.y = tc::pack_bf16(p[2], p[3]);
             o.z = tc::pack_bf16(p[4], p[5]); o.w = tc::pack_bf16(p[6], p[7]);
             *reinterpret_cast<uint4*>(Ps + c8 * (128 * 16) + tid * 16) = o;
         }
         m = mx;
+        rs_prev = rs;
         tc::fence_async_smem();
         tc::fence_before_sync();
         __syncthreads();
@@ -323,17 +351,18 @@ attn_fwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
 // after the exp/FMA phase of a half the issuing thread queues dV, dK (and dQ on the second half) of
 // THIS half and S^T, dP^T of the NEXT half back to back; Q / dO tiles are double buffered in shared
 // memory and staged through registers one tile ahead.
-template <int D>
+template <int D, bool DROP>
 __global__ void __launch_bounds__(256, 2)
 attn_bwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const bf16* __restrict__ Vb,
                 const bf16* __restrict__ dOb, const float* __restrict__ lse, const float* __restrict__ Dvec,
                 float* __restrict__ dQacc, float* __restrict__ dKh, float* __restrict__ dVh,
-                int S, int H, int Hkv, float scale, float scale_log2, int debug) {
+                int S, int H, int Hkv, float scale, float scale_log2, int debug, const DropCfg dc) {
     extern __shared__ __align__(1024) uint8_t sm[];
     __shared__ uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float nlse_s[2][128];    // -lse (log2 domain); -inf for padding queries
     __shared__ __align__(16) float D_s[2][128];
+    __shared__ __align__(16) uint32_t rk_s[2][128];   // DROP: per-query row keys of the tile
     constexpr int TILE_B = 128 * D * 2;
     constexpr uint32_t TM_COLS = (128 + 3 * D <= 256) ? 256 : 512;
     uint8_t* Kt = sm;
@@ -369,6 +398,7 @@ attn_bwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
         store_row<D>(half == 0 ? Qs : dOs, row, r);
         const float st0 = vq ? stat_src[row] : (half == 0 ? INFINITY : 0.f);
         if (half == 0) nlse_s[0][row] = -st0; else D_s[0][row] = st0;
+        if (DROP && half == 0) rk_s[0][row] = drop_rowkey(dc, (uint32_t)(stat_off + row));
         if (nq > 1) {                                // tile 1 -> registers
             const int qn = 128 + row;
             const bool v1 = qn < S;
@@ -475,6 +505,8 @@ attn_bwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
                 }
                 const float* nl_p = &nlse_s[bq][hq * 64 + c0];
                 const float* dd_p = &D_s[bq][hq * 64 + c0];
+                const uint32_t* rk_p = &rk_s[bq][hq * 64 + c0];
+                const uint32_t kterm = (uint32_t)key * 0x85EBCA6Bu;
 #pragma unroll
                 for (int c8 = 0; c8 < 4; ++c8) {
                     const float4 l0 = *reinterpret_cast<const float4*>(nl_p + c8 * 8);
@@ -487,7 +519,13 @@ attn_bwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
                         p[c] = ex2_approx(fmaf(st[c8 * 8 + c], scale_log2, nl[c]));
-                        ds[c] = p[c] * (dp[c8 * 8 + c] - dd[c]);          // unscaled; `scale` is applied to dQ / dK at the end
+                        if (DROP) {
+                            const float mk = (lowbias32(rk_p[c8 * 8 + c] ^ kterm) >= dc.thresh) ? dc.inv_keep : 0.f;
+                            ds[c] = p[c] * fmaf(dp[c8 * 8 + c], mk, -dd[c]);
+                            p[c] *= mk;                                   // P^T tile feeds dV with the dropped probabilities
+                        } else {
+                            ds[c] = p[c] * (dp[c8 * 8 + c] - dd[c]);      // unscaled; `scale` is applied to dQ / dK at the end
+                        }
                     }
                     uint4 o;
                     o.x = tc::pack_bf16(p[0], p[1]); o.y = tc::pack_bf16(p[2], p[3]);
@@ -501,6 +539,7 @@ attn_bwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
             if (hq == 0 && i + 1 < nq) {              // tile i+1: registers -> the other buffer; fetch tile i+2
                 store_row<D>((half == 0 ? Qs : dOs) + (bq ^ 1) * TILE_B, row, nreg);
                 if (half == 0) nlse_s[bq ^ 1][row] = -nstat; else D_s[bq ^ 1][row] = nstat;
+                if (DROP && half == 0) rk_s[bq ^ 1][row] = drop_rowkey(dc, (uint32_t)(stat_off + (i + 1) * 128 + row));
                 if (i + 2 < nq) {
                     const int qn = (i + 2) * 128 + row;
                     const bool vq = qn < S;
@@ -604,9 +643,18 @@ size_t gaot_attn_workspace_bytes(int64_t B, int64_t S, int32_t H, int32_t Hkv, i
     return attn_ws_bytes(B, S, H, Hkv, d);
 }
 
+static DropCfg make_drop(float p, uint64_t seed) {
+    DropCfg dc;
+    double t = (double)p * 4294967296.0;
+    dc.thresh = t >= 4294967295.0 ? 0xffffffffu : (uint32_t)t;
+    dc.seed_lo = (uint32_t)seed; dc.seed_hi = (uint32_t)(seed >> 32);
+    dc.inv_keep = p < 1.0f ? 1.0f / (1.0f - p) : 0.f;
+    return dc;
+}
+
 int gaot_attn_forward(const float* q, const float* k, const float* v, int64_t B, int64_t S, int32_t H,
-                      int32_t Hkv, int32_t d, const float* rope_freqs, void* ws, size_t ws_bytes, float* out,
-                      float* lse, void* stream) {
+                      int32_t Hkv, int32_t d, const float* rope_freqs, float dropout_p, uint64_t seed,
+                      void* ws, size_t ws_bytes, float* out, float* lse, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     int rc = attn_check(B, S, H, Hkv, d);
     if (rc) return rc;
@@ -614,26 +662,32 @@ int gaot_attn_forward(const float* q, const float* k, const float* v, int64_t B,
     if (!attn_carve(w, ws, ws_bytes, B, S, H, Hkv, d)) { set_error("attn_forward: workspace too small"); return GAOT_ERR_WORKSPACE; }
     rc = attn_prep_all(q, k, v, w, B, S, H, Hkv, d, rope_freqs, st);
     if (rc) return rc;
+    GAOT_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "attn: dropout_p must be in [0,1)");
+    GAOT_CHECK_ARG((int64_t)B * H * S < ((int64_t)1 << 32), "attn: B*H*S too large for the dropout counter");
     const float scale_log2 = (1.0f / sqrtf((float)d)) * 1.4426950408889634f;
+    const DropCfg dc = make_drop(dropout_p, seed);
+    const bool drop = dropout_p > 0.f;
     dim3 grid((unsigned)((S + 127) / 128), (unsigned)H, (unsigned)B);
     GAOT_TIME_KERNEL("attn_fwd", st, 4.0 * (double)B * H * (double)S * (double)S * d);
+#define GAOT_FWD_LAUNCH(DD, DR, SM)                                                                                   \
+    do { GAOT_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DD, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM))); \
+         attn_fwd_kernel<DD, DR><<<grid, 128, (SM), st>>>(w.Qb, w.Kb, w.Vb, out, lse, (int)S, H, Hkv, scale_log2, dc); } while (0)
     if (d == 32) {
         const size_t smem = 3 * 128 * 32 * 2 + 2 * 128 * 48 * 2 + 128 * 128 * 2;
-        GAOT_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attn_fwd_kernel<32><<<grid, 128, smem, st>>>(w.Qb, w.Kb, w.Vb, out, lse, (int)S, H, Hkv, scale_log2);
+        if (drop) GAOT_FWD_LAUNCH(32, true, smem); else GAOT_FWD_LAUNCH(32, false, smem);
     } else {
         const size_t smem = 3 * 128 * 64 * 2 + 2 * 128 * 80 * 2 + 128 * 128 * 2;
-        GAOT_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attn_fwd_kernel<64><<<grid, 128, smem, st>>>(w.Qb, w.Kb, w.Vb, out, lse, (int)S, H, Hkv, scale_log2);
+        if (drop) GAOT_FWD_LAUNCH(64, true, smem); else GAOT_FWD_LAUNCH(64, false, smem);
     }
+#undef GAOT_FWD_LAUNCH
     GAOT_LAUNCH_CHECK();
     return GAOT_OK;
 }
 
 int gaot_attn_backward(const float* q, const float* k, const float* v, const float* out, const float* d_out,
                        const float* lse, int64_t B, int64_t S, int32_t H, int32_t Hkv, int32_t d,
-                       const float* rope_freqs, void* ws, size_t ws_bytes, float* dq, float* dk, float* dv,
-                       void* stream) {
+                       const float* rope_freqs, float dropout_p, uint64_t seed, void* ws, size_t ws_bytes,
+                       float* dq, float* dk, float* dv, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     int rc = attn_check(B, S, H, Hkv, d);
     if (rc) return rc;
@@ -650,17 +704,20 @@ int gaot_attn_backward(const float* q, const float* k, const float* v, const flo
     dim3 grid((unsigned)((S + 127) / 128), (unsigned)H, (unsigned)B);
     {
     GAOT_TIME_KERNEL("attn_bwd", st, 10.0 * (double)B * H * (double)S * (double)S * d);
+    const DropCfg dc = make_drop(dropout_p, seed);
+    const bool drop = dropout_p > 0.f;
+#define GAOT_BWD_LAUNCH(DD, DR, SM)                                                                                   \
+    do { GAOT_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<DD, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM))); \
+         attn_bwd_kernel<DD, DR><<<grid, 256, (SM), st>>>(w.Qb, w.Kb, w.Vb, w.dOb, lse, w.Dvec, w.dQacc, w.dKh, w.dVh,    \
+                                                         (int)S, H, Hkv, scale, scale_log2, dbg, dc); } while (0)
     if (d == 32) {
         const size_t smem = 6 * 128 * 32 * 2 + 128 * 64 * 2 + 128 * 128 * 2;
-        GAOT_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attn_bwd_kernel<32><<<grid, 256, smem, st>>>(w.Qb, w.Kb, w.Vb, w.dOb, lse, w.Dvec, w.dQacc, w.dKh, w.dVh,
-                                                     (int)S, H, Hkv, scale, scale_log2, dbg);
+        if (drop) GAOT_BWD_LAUNCH(32, true, smem); else GAOT_BWD_LAUNCH(32, false, smem);
     } else {
         const size_t smem = 6 * 128 * 64 * 2 + 128 * 64 * 2 + 128 * 128 * 2;
-        GAOT_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attn_bwd_kernel<64><<<grid, 256, smem, st>>>(w.Qb, w.Kb, w.Vb, w.dOb, lse, w.Dvec, w.dQacc, w.dKh, w.dVh,
-                                                     (int)S, H, Hkv, scale, scale_log2, dbg);
+        if (drop) GAOT_BWD_LAUNCH(64, true, smem); else GAOT_BWD_LAUNCH(64, false, smem);
     }
+#undef GAOT_BWD_LAUNCH
     }
     GAOT_LAUNCH_CHECK();
     attn_bwd_post_kernel<<<nb256(B * S * H * (d / 8)), 256, 0, st>>>(w.dQacc, dq, B, S, H, H, d, rope_freqs);

@@ -92,13 +92,9 @@ class GroupQueryFlashAttention(nn.Module):
         lead = x.shape[:-2]
         x3 = x.reshape(-1, x.shape[-2], x.shape[-1])
         q, k, v = self.q_proj(x3), self.k_proj(x3), self.v_proj(x3)
-        if self.training and self.atten_dropout > 0.0:
-            # reference attn.py:122-126 applies dropout inside SDPA; the Philox dropout path of the
-            # tcgen05 kernel is not built yet -> fail loudly rather than silently change semantics
-            raise NotImplementedError("attention dropout > 0 in training mode is not supported yet: set "
-                                      "attn_config.atten_dropout=0.0 (or call .eval())")
+        dp = self.atten_dropout if self.training else 0.0          # reference attn.py:122-126
         freqs = self.rotary_emb.freqs if relative_positions is not None else None
-        o = ops.attention(q, k, v, self.num_heads, self.num_kv_heads, rope_freqs=freqs)
+        o = ops.attention(q, k, v, self.num_heads, self.num_kv_heads, rope_freqs=freqs, dropout_p=dp)
         return self.o_proj(o.to(x.dtype)).reshape(*lead, x.shape[-2], -1)
 
     @classmethod

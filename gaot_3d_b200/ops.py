@@ -350,7 +350,7 @@ def zscore_(feat: torch.Tensor) -> torch.Tensor:
 # ----------------------------------------------------------------------------- attention
 class _AttnFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, k, v, num_heads, num_kv_heads, freqs):
+    def forward(ctx, q, k, v, num_heads, num_kv_heads, freqs, dropout_p, seed):
         lib = _lib_()
         B, S, HD = q.shape
         d = HD // num_heads
@@ -362,16 +362,16 @@ class _AttnFn(torch.autograd.Function):
         wsb = lib.gaot_attn_workspace_bytes(B, S, num_heads, num_kv_heads, d)
         ws = _ws(wsb, dev)
         with torch.cuda.device(dev), _timed("attn_fwd", dev):
-            check(lib.gaot_attn_forward(_p(q), _p(k), _p(v), B, S, num_heads, num_kv_heads, d, _p(fr), _p(ws), wsb,
-                                        _p(out), _p(lse), _stream(dev)), "attn_forward")
+            check(lib.gaot_attn_forward(_p(q), _p(k), _p(v), B, S, num_heads, num_kv_heads, d, _p(fr), float(dropout_p),
+                                        int(seed), _p(ws), wsb, _p(out), _p(lse), _stream(dev)), "attn_forward")
         ctx.save_for_backward(q, k, v, out, lse, fr)
-        ctx.cfg = (B, S, num_heads, num_kv_heads, d)
+        ctx.cfg = (B, S, num_heads, num_kv_heads, d, float(dropout_p), int(seed))
         return out
 
     @staticmethod
     def backward(ctx, d_out):
         q, k, v, out, lse, fr = ctx.saved_tensors
-        B, S, H, Hkv, d = ctx.cfg
+        B, S, H, Hkv, d, dropout_p, seed = ctx.cfg
         lib = _lib_()
         dev = q.device
         d_out = d_out.to(torch.float32).contiguous()
@@ -380,15 +380,19 @@ class _AttnFn(torch.autograd.Function):
         ws = _ws(wsb, dev)
         with torch.cuda.device(dev), _timed("attn_bwd", dev):
             check(lib.gaot_attn_backward(_p(q), _p(k), _p(v), _p(out), _p(d_out), _p(lse), B, S, H, Hkv, d, _p(fr),
-                                         _p(ws), wsb, _p(dq), _p(dk), _p(dv), _stream(dev)), "attn_backward")
-        return dq, dk, dv, None, None, None
+                                         dropout_p, seed, _p(ws), wsb, _p(dq), _p(dk), _p(dv), _stream(dev)), "attn_backward")
+        return dq, dk, dv, None, None, None, None, None
 
 
-def attention(q, k, v, num_heads: int, num_kv_heads: int, rope_freqs: Optional[torch.Tensor] = None):
+def attention(q, k, v, num_heads: int, num_kv_heads: int, rope_freqs: Optional[torch.Tensor] = None,
+              dropout_p: float = 0.0, seed: Optional[int] = None):
     """softmax(QK^T/sqrt(d))V on token-major projections q [B,S,H*d], k/v [B,S,Hkv*d]
-    (reference attn.py:110-128), optional 1-D RoPE with the module's `freqs`."""
+    (reference attn.py:110-128), optional 1-D RoPE with the module's `freqs`, optional dropout on the
+    probabilities (counter-based mask; `seed` defaults to a draw from torch's CPU generator)."""
     _need_cuda(q, k, v)
-    return _AttnFn.apply(q, k, v, int(num_heads), int(num_kv_heads), rope_freqs)
+    if dropout_p > 0.0 and seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    return _AttnFn.apply(q, k, v, int(num_heads), int(num_kv_heads), rope_freqs, float(dropout_p), int(seed or 0))
 
 
 def launch_count() -> int:

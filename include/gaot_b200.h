@@ -159,10 +159,12 @@ size_t gaot_attn_workspace_bytes(int64_t B, int64_t S, int32_t H, int32_t Hkv, i
 int gaot_attn_forward(const float* q, const float* k, const float* v, int64_t B, int64_t S,
                       int32_t H, int32_t Hkv, int32_t d,
                       const float* rope_freqs /* [d/2] = RotaryEmbedding.freqs, NULL: no RoPE */,
+                      float dropout_p /* attn.py:122-126; 0 = off */, uint64_t dropout_seed,
                       void* ws, size_t ws_bytes, float* out, float* lse, void* stream);
 int gaot_attn_backward(const float* q, const float* k, const float* v, const float* out,
                        const float* d_out, const float* lse, int64_t B, int64_t S,
                        int32_t H, int32_t Hkv, int32_t d, const float* rope_freqs,
+                       float dropout_p, uint64_t dropout_seed,
                        void* ws, size_t ws_bytes, float* dq, float* dk, float* dv, void* stream);
 
 /* ------------------------------------------------------------------ host-buffer convenience (e2e arm)

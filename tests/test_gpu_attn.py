@@ -57,3 +57,28 @@ def test_attention_module_golden(tag):
         if n in g["d_state"]:
             l2, mx = relerr(p.grad, g["d_state"][n])
             assert l2 < 1.5e-2, (n, l2, mx)
+
+
+@pytest.mark.parametrize("B,S,H,Hkv,d,p", [(1, 384, 4, 4, 32, 0.1), (2, 200, 4, 2, 32, 0.3)])
+def test_attention_dropout_matches_oracle_mask(B, S, H, Hkv, d, p):
+    """Training-mode dropout (reference attn.py:122-126): the kernels' counter-based mask is restated in
+    oracle.attn.dropout_keep, so forward and backward are checked exactly like the p=0 case."""
+    from gaot_3d_b200 import ops
+    torch.manual_seed(3)
+    q, k, v = torch.randn(B, S, H * d), torch.randn(B, S, Hkv * d), torch.randn(B, S, Hkv * d)
+    seed = 0x1234_5678_9ABC_DEF1
+    qr, kr, vr = (t.double().requires_grad_(True) for t in (q, k, v))
+    ref = oattn.attention_core(qr, kr, vr, H, Hkv, False, dtype=torch.float64, dropout_p=p, seed=seed)
+    go = torch.randn_like(ref)
+    ref.backward(go)
+    keep = oattn.dropout_keep(B, H, S, p, seed)
+    assert abs(keep.float().mean().item() - (1 - p)) < 0.01
+    qd, kd, vd = (t.to(DEV).requires_grad_(True) for t in (q, k, v))
+    out = ops.attention(qd, kd, vd, H, Hkv, dropout_p=p, seed=seed)
+    out.backward(go.float().to(DEV))
+    for name, a, b in (("out", out, ref), ("dq", qd.grad, qr.grad), ("dk", kd.grad, kr.grad), ("dv", vd.grad, vr.grad)):
+        l2, mx = relerr(a, b)
+        assert l2 < 1e-2 and mx < 2.5e-2, f"{name}: rel l2 {l2:.3e}, rel max {mx:.3e}"
+    # different seeds -> different masks; module in train() mode runs and differs from eval()
+    out2 = ops.attention(qd, kd, vd, H, Hkv, dropout_p=p, seed=seed + 1)
+    assert (out2 - out).abs().max().item() > 1e-3
