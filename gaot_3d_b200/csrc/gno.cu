@@ -8,6 +8,10 @@ int gno_backward_fp32(const GnoArgs& a, const float* d_out, void* ws, size_t ws_
                       float* d_params, float* d_f, cudaStream_t st);
 size_t gno_backward_ws_bytes(int n_params);
 int gno_forward_bf16(const GnoArgs& a, void* ws, size_t ws_bytes, float* out, cudaStream_t st);
+bool gno_backward_bf16_supported(const GnoArgs& a);
+bool gno_forward_bf16_supported(const GnoArgs& a);
+int gno_backward_bf16(const GnoArgs& a, const float* d_out, void* ws, size_t ws_bytes, float* d_params, float* d_f,
+                      cudaStream_t st);
 }  // namespace gaot
 
 using namespace gaot;
@@ -54,7 +58,10 @@ int gaot_gno_forward(const float* y_pos, int64_t n_src, const float* x_pos, int6
     int rc = fill(a, y_pos, n_src, x_pos, nq, f_y, c_f, rowptr, csr_src, csr_qry, E, mlp, params, transform, reduce);
     if (rc) return rc;
     if (precision == 0) return gno_forward_fp32(a, ws, ws_bytes, out, (cudaStream_t)stream);
-    if (precision == 1) return gno_forward_bf16(a, ws, ws_bytes, out, (cudaStream_t)stream);
+    if (precision == 1) {
+        if (gno_forward_bf16_supported(a)) return gno_forward_bf16(a, ws, ws_bytes, out, (cudaStream_t)stream);
+        return gno_forward_fp32(a, ws, ws_bytes, out, (cudaStream_t)stream);     // outside the tcgen05 envelope: FP32 kernel
+    }
     set_error("gno: unknown precision %d", precision);
     return GAOT_ERR_INVALID;
 }
@@ -68,7 +75,9 @@ int gaot_gno_backward(const float* y_pos, int64_t n_src, const float* x_pos, int
     int rc = fill(a, y_pos, n_src, x_pos, nq, f_y, c_f, rowptr, csr_src, csr_qry, E, mlp, params, transform, reduce);
     if (rc) return rc;
     GAOT_CHECK_ARG(d_out != nullptr && d_params != nullptr, "gno_backward: null gradient buffers");
-    (void)precision;   // the backward recompute runs in FP32 on CUDA cores for both precisions (round 1)
+    // precision 1: tensor-core backward when the MLP fits its envelope, otherwise the FP32 recompute
+    if (precision == 1 && gno_backward_bf16_supported(a))
+        return gno_backward_bf16(a, d_out, ws, ws_bytes, d_params, d_f_y, (cudaStream_t)stream);
     return gno_backward_fp32(a, d_out, ws, ws_bytes, d_params, d_f_y, (cudaStream_t)stream);
 }
 

@@ -358,6 +358,12 @@ gno_bwd_reduce_kernel(const float* __restrict__ partial, int nparts, int n_param
     d_params[p] = s;
 }
 
+int gno_bwd_reduce(const float* partial, int nparts, int n_params, float* d_params, cudaStream_t st) {
+    gno_bwd_reduce_kernel<<<(n_params + 255) / 256, 256, 0, st>>>(partial, nparts, n_params, d_params);
+    GAOT_LAUNCH_CHECK();
+    return GAOT_OK;
+}
+
 size_t gno_backward_ws_bytes(int n_params) { return align_up((size_t)kNumSMs * n_params * sizeof(float)) + 256; }
 
 int gno_backward_fp32(const GnoArgs& a_in, const float* d_out, void* ws, size_t ws_bytes,

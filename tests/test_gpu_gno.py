@@ -186,6 +186,16 @@ def test_gno_bf16_tensor_core_path(strategy, dec):
     fr = f.double().requires_grad_(True)
     ogno.integral_transform(ypos.double(), xpos.double(), ei, fr, wr, [b.double() for b in bs]).backward(g)
     out.backward(g.float().to(DEV))
-    assert ((fd.grad.double().cpu() - fr.grad).norm() / fr.grad.norm()).item() < 1e-2
+    br = None
+    e = ((fd.grad.double().cpu() - fr.grad).norm() / fr.grad.norm()).item()
+    assert e < 2e-2, ("d_f", e)
     for i in range(len(ws)):
-        assert ((wd[i].grad.double().cpu() - wr[i].grad).norm() / wr[i].grad.norm()).item() < 1e-2
+        e = ((wd[i].grad.double().cpu() - wr[i].grad).norm() / wr[i].grad.norm()).item()
+        assert e < 2e-2, (f"dW{i}", e)
+    # biases: compare against fp64 autograd as well
+    wr2 = [w.double().requires_grad_(True) for w in ws]
+    br2 = [b.double().requires_grad_(True) for b in bs]
+    ogno.integral_transform(ypos.double(), xpos.double(), ei, f.double(), wr2, br2).backward(g)
+    for i in range(len(bs)):
+        e = ((bd[i].grad.double().cpu() - br2[i].grad).norm() / br2[i].grad.norm()).item()
+        assert e < 2e-2, (f"db{i}", e)
