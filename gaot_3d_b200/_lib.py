@@ -50,6 +50,26 @@ _SIGS = {
     "gaot_attn_forward": (c_int, [P, P, P, c_int64, c_int64, c_int32, c_int32, c_int32, P, c_float, c_uint64, P, c_size_t, P, P, P]),
     "gaot_attn_backward": (c_int, [P, P, P, P, P, P, c_int64, c_int64, c_int32, c_int32, c_int32, P, c_float, c_uint64,
                                    P, c_size_t, P, P, P, P]),
+    "gaot_linear_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "gaot_linear_forward": (c_int, [P, c_int, c_int64, P, c_int64, c_int64, P, c_int, c_int64, c_int64, c_int64,
+                                    P, P, c_int64, P, c_int, c_int64, P, c_size_t, P]),
+    "gaot_linear_backward_input": (c_int, [P, c_int, c_int64, P, c_int, c_int64, c_int64, c_int64, P, c_int64,
+                                           P, c_int, c_int64, c_int, P, c_size_t, P]),
+    "gaot_linear_backward_weight": (c_int, [P, c_int, c_int64, P, c_int, c_int64, c_int64, c_int64, c_int64,
+                                            P, c_int64, c_int, P, c_size_t, P]),
+    "gaot_cast_bf16": (c_int, [P, P, c_int64, P]),
+    "gaot_rmsnorm_forward": (c_int, [P, P, c_int64, c_int32, c_float, P, P, P, P]),
+    "gaot_rmsnorm_backward_workspace_bytes": (c_size_t, [c_int32]),
+    "gaot_rmsnorm_backward": (c_int, [P, P, P, P, P, c_int64, c_int32, P, P, P, c_size_t, P]),
+    "gaot_colsum_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "gaot_colsum": (c_int, [P, c_int64, c_int64, P, P, c_size_t, P]),
+    "gaot_swiglu_forward": (c_int, [P, c_int64, c_int32, P, P]),
+    "gaot_swiglu_backward": (c_int, [P, P, c_int64, c_int32, P, P]),
+    "gaot_attn_packed_bytes": (c_size_t, [c_int64, c_int64, c_int32, c_int32, c_int32]),
+    "gaot_attn_fused_forward": (c_int, [P, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, P, c_float, c_uint64, P, P, P, P]),
+    "gaot_attn_fused_backward_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32, c_int32]),
+    "gaot_attn_fused_backward": (c_int, [P, P, P, P, c_int64, c_int64, c_int32, c_int32, c_int32, P, c_float, c_uint64,
+                                         P, c_size_t, P, c_int64, P]),
     "gaot_radius_host": (c_int, [P, c_int64, P, c_int64, c_double, c_int, P, P, POINTER(c_int64)]),
     "gaot_knn_host": (c_int, [P, c_int64, P, c_int64, c_int, P, P, POINTER(c_int64)]),
     "gaot_tc_probe": (c_int, [P, P, P, c_int, c_int, c_int, P]),

@@ -62,6 +62,94 @@ attn_prep_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t 
     *reinterpret_cast<uint4*>(dst + ((b * nh + h) * S + s) * d + ch * 8) = o;
 }
 
+// fused-projection variant: qkv bf16 [B*S, ld] (columns: H*d of q | Hkv*d of k | Hkv*d of v, the output of
+// one [Wq;Wk;Wv] GEMM) -> Qb [B,H,S,d], Kb, Vb [B,Hkv,S,d] bf16 with RoPE on q and k; one launch.
+__device__ __forceinline__ void unpack_bf16x8(const uint4& v, float (&f)[8]) {
+    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(p[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__global__ void __launch_bounds__(256)
+attn_pack_qkv_kernel(const bf16* __restrict__ qkv, int64_t ld, bf16* __restrict__ Qb, bf16* __restrict__ Kb,
+                     bf16* __restrict__ Vb, int64_t B, int64_t S, int H, int Hkv, int d, const float* __restrict__ freqs) {
+    const int cpr = d >> 3, nh = H + 2 * Hkv;
+    const int64_t total = B * S * nh * cpr;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int ch = (int)(idx % cpr);
+    const int hh = (int)((idx / cpr) % nh);
+    const int64_t s = (idx / ((int64_t)cpr * nh)) % S;
+    const int64_t b = idx / ((int64_t)cpr * nh * S);
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(qkv + (b * S + s) * ld + (int64_t)hh * d + ch * 8));
+    bf16* dst; int h, nhd; bool rope;
+    if (hh < H) { dst = Qb; h = hh; nhd = H; rope = true; }
+    else if (hh < H + Hkv) { dst = Kb; h = hh - H; nhd = Hkv; rope = true; }
+    else { dst = Vb; h = hh - H - Hkv; nhd = Hkv; rope = false; }
+    uint4 o = raw;
+    if (rope && freqs) {
+        float x[8];
+        unpack_bf16x8(raw, x);
+        rope8<true>(x, (int)s, ch * 8, freqs, false);
+        o.x = tc::pack_bf16(x[0], x[1]); o.y = tc::pack_bf16(x[2], x[3]);
+        o.z = tc::pack_bf16(x[4], x[5]); o.w = tc::pack_bf16(x[6], x[7]);
+    }
+    *reinterpret_cast<uint4*>(dst + ((b * nhd + h) * S + s) * d + ch * 8) = o;
+}
+
+// bf16 variant of the backward prep (fused block: O and dO arrive token-major in bf16)
+__global__ void __launch_bounds__(256)
+attn_bwd_prep_bf16_kernel(const bf16* __restrict__ dO, const bf16* __restrict__ O, bf16* __restrict__ dOb,
+                          float* __restrict__ Dvec, int64_t B, int64_t S, int H, int d) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // (b, s, h)
+    if (idx >= B * S * H) return;
+    const int h = (int)(idx % H);
+    const int64_t s = (idx / H) % S, b = idx / ((int64_t)H * S);
+    const bf16* pd = dO + idx * d;
+    const bf16* po = O + idx * d;
+    bf16* out = dOb + ((b * H + h) * S + s) * d;
+    float acc = 0.f;
+    for (int c = 0; c < d; c += 8) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(pd + c)), o = __ldg(reinterpret_cast<const uint4*>(po + c));
+        float fa[8], fo[8];
+        unpack_bf16x8(a, fa); unpack_bf16x8(o, fo);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc = fmaf(fa[i], fo[i], acc);
+        *reinterpret_cast<uint4*>(out + c) = a;
+    }
+    Dvec[(b * H + h) * S + s] = acc;
+}
+
+// fused-block backward post: per-head fp32 dQ / dK / dV -> ONE bf16 token-major [B*S, ld] gradient of the fused
+// qkv projection output (GQA group summed, RoPE undone), ready to be the A operand of the dX / dW GEMMs.
+__global__ void __launch_bounds__(256)
+attn_bwd_post_qkv_kernel(const float* __restrict__ dQh, const float* __restrict__ dKh, const float* __restrict__ dVh,
+                         bf16* __restrict__ out, int64_t ld, int64_t B, int64_t S, int H, int Hkv, int d,
+                         const float* __restrict__ freqs) {
+    const int cpr = d >> 3, nh = H + 2 * Hkv;
+    const int64_t total = B * S * nh * cpr;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int ch = (int)(idx % cpr);
+    const int hh = (int)((idx / cpr) % nh);
+    const int64_t s = (idx / ((int64_t)cpr * nh)) % S;
+    const int64_t b = idx / ((int64_t)cpr * nh * S);
+    const float* src; int h0, rep; bool rope;
+    if (hh < H) { src = dQh; h0 = hh; rep = 1; rope = true; }
+    else if (hh < H + Hkv) { src = dKh; rep = H / Hkv; h0 = (hh - H) * rep; rope = true; }
+    else { src = dVh; rep = H / Hkv; h0 = (hh - H - Hkv) * rep; rope = false; }
+    float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < rep; ++r) {
+        const float* p = src + ((b * H + h0 + r) * S + s) * d + ch * 8;
+        const float4 v0 = *reinterpret_cast<const float4*>(p), v1 = *reinterpret_cast<const float4*>(p + 4);
+        x[0] += v0.x; x[1] += v0.y; x[2] += v0.z; x[3] += v0.w; x[4] += v1.x; x[5] += v1.y; x[6] += v1.z; x[7] += v1.w;
+    }
+    if (rope && freqs) rope8<true>(x, (int)s, ch * 8, freqs, true);
+    uint4 o;
+    o.x = tc::pack_bf16(x[0], x[1]); o.y = tc::pack_bf16(x[2], x[3]);
+    o.z = tc::pack_bf16(x[4], x[5]); o.w = tc::pack_bf16(x[6], x[7]);
+    *reinterpret_cast<uint4*>(out + (b * S + s) * ld + (int64_t)hh * d + ch * 8) = o;
+}
+
 // backward prep: dO -> bf16 [B,H,S,d] and Dvec[b,h,s] = sum_c dO*O
 __global__ void __launch_bounds__(256)
 attn_bwd_prep_kernel(const float* __restrict__ dO, const float* __restrict__ O, bf16* __restrict__ dOb,
@@ -159,7 +247,7 @@ __device__ __forceinline__ bool drop_keep(const DropCfg& dc, uint32_t rowkey, ui
 template <int D, bool DROP>
 __global__ void __launch_bounds__(128, 2)
 attn_fwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const bf16* __restrict__ Vb,
-                float* __restrict__ out, float* __restrict__ lse, int S, int H, int Hkv, float scale_log2, const DropCfg dc) {
+                void* __restrict__ out_v, int out_bf16, float* __restrict__ lse, int S, int H, int Hkv, float scale_log2, const DropCfg dc) {
     extern __shared__ __align__(1024) uint8_t sm[];
     __shared__ uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
@@ -333,10 +421,22 @@ attn_fwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
     }
     if (valid_q) {
         const float inv = 1.0f / l;
-        float* o = out + ((size_t)b * S + q) * (H * D) + h * D;
+        const size_t ooff = ((size_t)b * S + q) * (H * D) + h * D;
+        if (out_bf16) {
+            bf16* o = reinterpret_cast<bf16*>(out_v) + ooff;
 #pragma unroll
-        for (int c = 0; c < D; c += 4)
-            *reinterpret_cast<float4*>(o + c) = make_float4(O[c] * inv, O[c + 1] * inv, O[c + 2] * inv, O[c + 3] * inv);
+            for (int c = 0; c < D; c += 8) {
+                uint4 pk;
+                pk.x = tc::pack_bf16(O[c] * inv, O[c + 1] * inv); pk.y = tc::pack_bf16(O[c + 2] * inv, O[c + 3] * inv);
+                pk.z = tc::pack_bf16(O[c + 4] * inv, O[c + 5] * inv); pk.w = tc::pack_bf16(O[c + 6] * inv, O[c + 7] * inv);
+                *reinterpret_cast<uint4*>(o + c) = pk;
+            }
+        } else {
+            float* o = reinterpret_cast<float*>(out_v) + ooff;
+#pragma unroll
+            for (int c = 0; c < D; c += 4)
+                *reinterpret_cast<float4*>(o + c) = make_float4(O[c] * inv, O[c + 1] * inv, O[c + 2] * inv, O[c + 3] * inv);
+        }
         lse[((size_t)b * H + h) * S + q] = m + log2f(l);
     }
     tc::fence_before_sync();
@@ -652,6 +752,30 @@ static DropCfg make_drop(float p, uint64_t seed) {
     return dc;
 }
 
+static int attn_launch_fwd(const AttnWs& w, int64_t B, int64_t S, int H, int Hkv, int d, float dropout_p, uint64_t seed,
+                           void* out, int out_bf16, float* lse, cudaStream_t st) {
+    GAOT_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "attn: dropout_p must be in [0,1)");
+    GAOT_CHECK_ARG((int64_t)B * H * S < ((int64_t)1 << 32), "attn: B*H*S too large for the dropout counter");
+    const float scale_log2 = (1.0f / sqrtf((float)d)) * 1.4426950408889634f;
+    const DropCfg dc = make_drop(dropout_p, seed);
+    const bool drop = dropout_p > 0.f;
+    dim3 grid((unsigned)((S + 127) / 128), (unsigned)H, (unsigned)B);
+    GAOT_TIME_KERNEL("attn_fwd", st, 4.0 * (double)B * H * (double)S * (double)S * d);
+#define GAOT_FWD_LAUNCH(DD, DR, SM)                                                                                   \
+    do { GAOT_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DD, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM))); \
+         attn_fwd_kernel<DD, DR><<<grid, 128, (SM), st>>>(w.Qb, w.Kb, w.Vb, out, out_bf16, lse, (int)S, H, Hkv, scale_log2, dc); } while (0)
+    if (d == 32) {
+        const size_t smem = 3 * 128 * 32 * 2 + 2 * 128 * 48 * 2 + 128 * 128 * 2;
+        if (drop) GAOT_FWD_LAUNCH(32, true, smem); else GAOT_FWD_LAUNCH(32, false, smem);
+    } else {
+        const size_t smem = 3 * 128 * 64 * 2 + 2 * 128 * 80 * 2 + 128 * 128 * 2;
+        if (drop) GAOT_FWD_LAUNCH(64, true, smem); else GAOT_FWD_LAUNCH(64, false, smem);
+    }
+#undef GAOT_FWD_LAUNCH
+    GAOT_LAUNCH_CHECK();
+    return GAOT_OK;
+}
+
 int gaot_attn_forward(const float* q, const float* k, const float* v, int64_t B, int64_t S, int32_t H,
                       int32_t Hkv, int32_t d, const float* rope_freqs, float dropout_p, uint64_t seed,
                       void* ws, size_t ws_bytes, float* out, float* lse, void* stream) {
@@ -662,24 +786,32 @@ int gaot_attn_forward(const float* q, const float* k, const float* v, int64_t B,
     if (!attn_carve(w, ws, ws_bytes, B, S, H, Hkv, d)) { set_error("attn_forward: workspace too small"); return GAOT_ERR_WORKSPACE; }
     rc = attn_prep_all(q, k, v, w, B, S, H, Hkv, d, rope_freqs, st);
     if (rc) return rc;
-    GAOT_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "attn: dropout_p must be in [0,1)");
-    GAOT_CHECK_ARG((int64_t)B * H * S < ((int64_t)1 << 32), "attn: B*H*S too large for the dropout counter");
-    const float scale_log2 = (1.0f / sqrtf((float)d)) * 1.4426950408889634f;
+    return attn_launch_fwd(w, B, S, H, Hkv, d, dropout_p, seed, out, 0, lse, st);
+}
+
+// core backward on prepared operands: w.Qb/Kb/Vb/dOb/Dvec filled -> w.dQacc / dKh / dVh (fp32, per head)
+static int attn_launch_bwd(const AttnWs& w, const float* lse, int64_t B, int64_t S, int H, int Hkv, int d,
+                           float dropout_p, uint64_t seed, cudaStream_t st) {
+    GAOT_CUDA(cudaMemsetAsync(w.dQacc, 0, (size_t)B * H * S * d * sizeof(float), st));
+    const float scale = 1.0f / sqrtf((float)d), scale_log2 = scale * 1.4426950408889634f;
+    const char* dbg_env = getenv("GAOT_ATTN_DEBUG");
+    const int dbg = dbg_env ? atoi(dbg_env) : 0;
+    dim3 grid((unsigned)((S + 127) / 128), (unsigned)H, (unsigned)B);
+    GAOT_TIME_KERNEL("attn_bwd", st, 10.0 * (double)B * H * (double)S * (double)S * d);
     const DropCfg dc = make_drop(dropout_p, seed);
     const bool drop = dropout_p > 0.f;
-    dim3 grid((unsigned)((S + 127) / 128), (unsigned)H, (unsigned)B);
-    GAOT_TIME_KERNEL("attn_fwd", st, 4.0 * (double)B * H * (double)S * (double)S * d);
-#define GAOT_FWD_LAUNCH(DD, DR, SM)                                                                                   \
-    do { GAOT_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DD, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM))); \
-         attn_fwd_kernel<DD, DR><<<grid, 128, (SM), st>>>(w.Qb, w.Kb, w.Vb, out, lse, (int)S, H, Hkv, scale_log2, dc); } while (0)
+#define GAOT_BWD_LAUNCH(DD, DR, SM)                                                                                   \
+    do { GAOT_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<DD, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM))); \
+         attn_bwd_kernel<DD, DR><<<grid, 256, (SM), st>>>(w.Qb, w.Kb, w.Vb, w.dOb, lse, w.Dvec, w.dQacc, w.dKh, w.dVh,    \
+                                                         (int)S, H, Hkv, scale, scale_log2, dbg, dc); } while (0)
     if (d == 32) {
-        const size_t smem = 3 * 128 * 32 * 2 + 2 * 128 * 48 * 2 + 128 * 128 * 2;
-        if (drop) GAOT_FWD_LAUNCH(32, true, smem); else GAOT_FWD_LAUNCH(32, false, smem);
+        const size_t smem = 6 * 128 * 32 * 2 + 128 * 64 * 2 + 128 * 128 * 2;
+        if (drop) GAOT_BWD_LAUNCH(32, true, smem); else GAOT_BWD_LAUNCH(32, false, smem);
     } else {
-        const size_t smem = 3 * 128 * 64 * 2 + 2 * 128 * 80 * 2 + 128 * 128 * 2;
-        if (drop) GAOT_FWD_LAUNCH(64, true, smem); else GAOT_FWD_LAUNCH(64, false, smem);
+        const size_t smem = 6 * 128 * 64 * 2 + 128 * 64 * 2 + 128 * 128 * 2;
+        if (drop) GAOT_BWD_LAUNCH(64, true, smem); else GAOT_BWD_LAUNCH(64, false, smem);
     }
-#undef GAOT_FWD_LAUNCH
+#undef GAOT_BWD_LAUNCH
     GAOT_LAUNCH_CHECK();
     return GAOT_OK;
 }
@@ -697,34 +829,68 @@ int gaot_attn_backward(const float* q, const float* k, const float* v, const flo
     if (rc) return rc;
     attn_bwd_prep_kernel<<<nb256(B * S * H), 256, 0, st>>>(d_out, out, w.dOb, w.Dvec, B, S, H, d);
     GAOT_LAUNCH_CHECK();
-    GAOT_CUDA(cudaMemsetAsync(w.dQacc, 0, (size_t)B * H * S * d * sizeof(float), st));
-    const float scale = 1.0f / sqrtf((float)d), scale_log2 = scale * 1.4426950408889634f;
-    const char* dbg_env = getenv("GAOT_ATTN_DEBUG");
-    const int dbg = dbg_env ? atoi(dbg_env) : 0;
-    dim3 grid((unsigned)((S + 127) / 128), (unsigned)H, (unsigned)B);
-    {
-    GAOT_TIME_KERNEL("attn_bwd", st, 10.0 * (double)B * H * (double)S * (double)S * d);
-    const DropCfg dc = make_drop(dropout_p, seed);
-    const bool drop = dropout_p > 0.f;
-#define GAOT_BWD_LAUNCH(DD, DR, SM)                                                                                   \
-    do { GAOT_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<DD, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM))); \
-         attn_bwd_kernel<DD, DR><<<grid, 256, (SM), st>>>(w.Qb, w.Kb, w.Vb, w.dOb, lse, w.Dvec, w.dQacc, w.dKh, w.dVh,    \
-                                                         (int)S, H, Hkv, scale, scale_log2, dbg, dc); } while (0)
-    if (d == 32) {
-        const size_t smem = 6 * 128 * 32 * 2 + 128 * 64 * 2 + 128 * 128 * 2;
-        if (drop) GAOT_BWD_LAUNCH(32, true, smem); else GAOT_BWD_LAUNCH(32, false, smem);
-    } else {
-        const size_t smem = 6 * 128 * 64 * 2 + 128 * 64 * 2 + 128 * 128 * 2;
-        if (drop) GAOT_BWD_LAUNCH(64, true, smem); else GAOT_BWD_LAUNCH(64, false, smem);
-    }
-#undef GAOT_BWD_LAUNCH
-    }
-    GAOT_LAUNCH_CHECK();
+    rc = attn_launch_bwd(w, lse, B, S, H, Hkv, d, dropout_p, seed, st);
+    if (rc) return rc;
     attn_bwd_post_kernel<<<nb256(B * S * H * (d / 8)), 256, 0, st>>>(w.dQacc, dq, B, S, H, H, d, rope_freqs);
     GAOT_LAUNCH_CHECK();
     attn_bwd_post_kernel<<<nb256(B * S * Hkv * (d / 8)), 256, 0, st>>>(w.dKh, dk, B, S, H, Hkv, d, rope_freqs);
     GAOT_LAUNCH_CHECK();
     attn_bwd_post_kernel<<<nb256(B * S * Hkv * (d / 8)), 256, 0, st>>>(w.dVh, dv, B, S, H, Hkv, d, nullptr);
+    GAOT_LAUNCH_CHECK();
+    return GAOT_OK;
+}
+
+// ---- fused-block flavour: operands stay in the kernels' own bf16 per-head layout between forward and backward ----
+size_t gaot_attn_packed_bytes(int64_t B, int64_t S, int32_t H, int32_t Hkv, int32_t d) {
+    return align_up((size_t)B * H * S * d * 2) + 2 * align_up((size_t)B * Hkv * S * d * 2);
+}
+
+static void attn_packed_ptrs(AttnWs& w, void* packed, int64_t B, int64_t S, int H, int Hkv, int d) {
+    char* p = (char*)packed;
+    w.Qb = (bf16*)p; p += align_up((size_t)B * H * S * d * 2);
+    w.Kb = (bf16*)p; p += align_up((size_t)B * Hkv * S * d * 2);
+    w.Vb = (bf16*)p;
+}
+
+int gaot_attn_fused_forward(const void* qkv, int64_t ld, int64_t B, int64_t S, int32_t H, int32_t Hkv, int32_t d,
+                            const float* rope_freqs, float dropout_p, uint64_t seed,
+                            void* packed, void* out, float* lse, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = attn_check(B, S, H, Hkv, d);
+    if (rc) return rc;
+    GAOT_CHECK_ARG(qkv && packed && out && lse && ld % 8 == 0, "attn_fused_forward: bad pointer / ld");
+    AttnWs w{};
+    attn_packed_ptrs(w, packed, B, S, H, Hkv, d);
+    attn_pack_qkv_kernel<<<nb256(B * S * (H + 2 * Hkv) * (d / 8)), 256, 0, st>>>((const bf16*)qkv, ld, w.Qb, w.Kb, w.Vb, B, S, H, Hkv, d, rope_freqs);
+    GAOT_LAUNCH_CHECK();
+    return attn_launch_fwd(w, B, S, H, Hkv, d, dropout_p, seed, out, 1, lse, st);
+}
+
+size_t gaot_attn_fused_backward_workspace_bytes(int64_t B, int64_t S, int32_t H, int32_t d) {
+    const size_t qe = (size_t)B * H * S * d;
+    return align_up(qe * 2) + align_up((size_t)B * H * S * 4) + 3 * align_up(qe * 4) + 1024;
+}
+
+int gaot_attn_fused_backward(const void* packed, const void* out, const void* d_out, const float* lse,
+                             int64_t B, int64_t S, int32_t H, int32_t Hkv, int32_t d, const float* rope_freqs,
+                             float dropout_p, uint64_t seed, void* ws, size_t ws_bytes,
+                             void* d_qkv, int64_t ld, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = attn_check(B, S, H, Hkv, d);
+    if (rc) return rc;
+    GAOT_CHECK_ARG(packed && out && d_out && lse && d_qkv && ld % 8 == 0, "attn_fused_backward: bad pointer / ld");
+    AttnWs w{};
+    attn_packed_ptrs(w, const_cast<void*>(packed), B, S, H, Hkv, d);
+    Arena ar(ws, ws_bytes);
+    const size_t qe = (size_t)B * H * S * d;
+    w.dOb = ar.take<bf16>(qe); w.Dvec = ar.take<float>((size_t)B * H * S);
+    w.dQacc = ar.take<float>(qe); w.dKh = ar.take<float>(qe); w.dVh = ar.take<float>(qe);
+    if (!ar.ok()) { set_error("attn_fused_backward: workspace too small"); return GAOT_ERR_WORKSPACE; }
+    attn_bwd_prep_bf16_kernel<<<nb256(B * S * H), 256, 0, st>>>((const bf16*)d_out, (const bf16*)out, w.dOb, w.Dvec, B, S, H, d);
+    GAOT_LAUNCH_CHECK();
+    rc = attn_launch_bwd(w, lse, B, S, H, Hkv, d, dropout_p, seed, st);
+    if (rc) return rc;
+    attn_bwd_post_qkv_kernel<<<nb256(B * S * (H + 2 * Hkv) * (d / 8)), 256, 0, st>>>(w.dQacc, w.dKh, w.dVh, (bf16*)d_qkv, ld, B, S, H, Hkv, d, rope_freqs);
     GAOT_LAUNCH_CHECK();
     return GAOT_OK;
 }

@@ -1,0 +1,428 @@
+// dense.cu -- token-level dense layers of the latent transformer on tcgen05 tensor cores.
+// Replaces the fp32 cuBLAS SGEMMs behind nn.Linear in reference src/model/layers/attn.py
+// (q/k/v/o_proj :104-106,:129; FFN w1/w2/w3 :163; skip_proj :223) and gaot_3d.py:205 (patch_linear):
+// with allow_tf32 = False those run on the FP32 SIMT pipe (~30 ms of a 70 ms step at S = 16384).
+//
+// One kernel, C[M,N] = sum_k A(m,k) * B(n,k), BF16 operands / FP32 accumulation in TMEM.  Operands
+// stay in their natural row-major global layout; the loader converts fp32 -> bf16 on the fly and writes
+// "chunk-major" shared tiles (tc05.cuh) that serve as K-major or MN-major tensor-core operands, so the
+// three products of a linear layer need no transposed copies:
+//     forward   y  = x  W^T     A = x  [M,K]  K-major     B = W [N,K]  K-major
+//     d input   dx = dy W       A = dy [M,N]  K-major     B = W [N,K]  MN-major (contraction over N)
+//     d weight  dW = dy^T x     A = dy [M,N]  MN-major    B = x [M,K]  MN-major (contraction over M, split-K)
+// CTA = 128x128 output tile, 256 threads: all threads stage operands (coalesced float4 loads, 8-byte
+// conflict-free shared stores into slabs padded by 16 B), one elected thread issues tcgen05.mma
+// (4 x K16 per 64-deep block) into a 3-stage ring released by tcgen05.commit -> mbarrier; 2 CTAs/SM.
+// Epilogue: tcgen05.ld -> warp-private XOR-swizzled transpose -> coalesced 128 B row segments with
+// fused bias / residual / accumulate, fp32 or bf16 output.
+#include "common.cuh"
+#include "tc05.cuh"
+#include <algorithm>
+
+namespace gaot {
+
+using bf16 = __nv_bfloat16;
+
+namespace dn {
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3, THREADS = 256;
+constexpr uint32_t SLAB_K = 128 * 16 + 16;      // K-major operand: 8 slabs (one per 8-wide K chunk) of 128 rows
+constexpr uint32_t SLAB_MN = 64 * 16 + 16;      // MN-major operand: 16 slabs (one per 8-wide M/N chunk) of 64 K rows
+constexpr uint32_t OP_BYTES = 16 * SLAB_MN;     // 16640 >= 8 * SLAB_K = 16512
+constexpr uint32_t STAGE_BYTES = 2 * OP_BYTES;
+constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES;
+}
+
+struct GemmArgs {
+    const void* A; const void* A2; const void* B;
+    int64_t lda, lda2, ldb;
+    int64_t M, N, K;            // output rows, output columns, contraction length
+    int64_t k_split;            // contraction index where A switches to A2 (K-major A only; multiple of BK), or K
+    const float* bias;          // [N] or null
+    const float* residual;      // [M, ldr] or null
+    int64_t ldr;
+    void* C; int64_t ldc;
+    int c_bf16;                 // output dtype
+    int accumulate;             // C += result (fp32 output only)
+    int kb_per_split;           // split-K: K blocks per blockIdx.z; partial results go to `partial`
+    float* partial;             // [splits, M, N] fp32 or null
+};
+
+// ---- operand staging: global (row-major, fp32 or bf16) -> registers -> bf16 chunk-major shared tile ----
+// K-major tile: 128 (M/N) rows x 64 contraction columns.  MN-major tile: 64 contraction rows x 128 (M/N) columns.
+template <typename T, bool MN> struct Stager;
+
+template <bool MN> struct Stager<float, MN> {
+    float4 r[8];
+    // row-major source: element (row, col) at src[row * ld + col]
+    __device__ __forceinline__ void load(const float* __restrict__ src, int64_t ld, int64_t row0, int64_t col0,
+                                         int64_t row_lim, int64_t col_lim, int tid) {
+        constexpr int F4_PER_ROW = MN ? 32 : 16;
+        constexpr int ROWS_PER_PASS = dn::THREADS / F4_PER_ROW;
+        const int f4 = tid % F4_PER_ROW, rr = tid / F4_PER_ROW;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            const int64_t row = row0 + p * ROWS_PER_PASS + rr, col = col0 + f4 * 4;
+            if (row < row_lim && col < col_lim)      // col_lim is a multiple of 4 (checked by the host)
+                r[p] = __ldg(reinterpret_cast<const float4*>(src + row * ld + col));
+            else
+                r[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    __device__ __forceinline__ void store(uint8_t* tile, int tid) const {
+        constexpr int F4_PER_ROW = MN ? 32 : 16;
+        constexpr int ROWS_PER_PASS = dn::THREADS / F4_PER_ROW;
+        constexpr uint32_t SLAB = MN ? dn::SLAB_MN : dn::SLAB_K;
+        const int f4 = tid % F4_PER_ROW, rr = tid / F4_PER_ROW;
+        uint8_t* base = tile + (f4 >> 1) * SLAB + (f4 & 1) * 8;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            uint2 v;
+            v.x = tc::pack_bf16(r[p].x, r[p].y);
+            v.y = tc::pack_bf16(r[p].z, r[p].w);
+            *reinterpret_cast<uint2*>(base + (p * ROWS_PER_PASS + rr) * 16) = v;
+        }
+    }
+};
+
+// bf16 sources need no conversion: cp.async (LDGSTS) lands 16-byte chunks directly in the tile, so several
+// K blocks stay in flight without holding registers (src-size 0 zero-fills out-of-range chunks).
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr, bool valid) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(saddr), "l"(gptr), "r"(valid ? 16u : 0u) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+template <bool MN>
+__device__ __forceinline__ void stage_async(const bf16* __restrict__ src, int64_t ld, int64_t row0, int64_t col0,
+                                            int64_t row_lim, int64_t col_lim, uint32_t tile_saddr, int tid) {
+    constexpr int CH_PER_ROW = MN ? 16 : 8;
+    constexpr int ROWS_PER_PASS = dn::THREADS / CH_PER_ROW;
+    constexpr uint32_t SLAB = MN ? dn::SLAB_MN : dn::SLAB_K;
+    const int ch = tid % CH_PER_ROW, rr = tid / CH_PER_ROW;
+    const int64_t col = col0 + ch * 8;
+    const uint32_t base = tile_saddr + ch * SLAB;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int r = p * ROWS_PER_PASS + rr;
+        const int64_t row = row0 + r;
+        const bool ok = row < row_lim && col < col_lim;
+        cp_async16(base + r * 16, ok ? (const void*)(src + row * ld + col) : (const void*)src, ok);
+    }
+}
+
+template <typename T> struct is_bf16 { static constexpr bool value = false; };
+template <> struct is_bf16<bf16> { static constexpr bool value = true; };
+
+template <typename TA, typename TB, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(dn::THREADS, 2)
+gemm_tc_kernel(const GemmArgs g) {
+    extern __shared__ __align__(128) uint8_t sm[];
+    __shared__ uint64_t mbar_free[dn::STAGES];
+    __shared__ uint64_t mbar_done;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t n0 = (int64_t)blockIdx.x * dn::BN, m0 = (int64_t)blockIdx.y * dn::BM;
+    const int nkb_total = (int)((g.K + dn::BK - 1) / dn::BK);
+    const int kb0 = blockIdx.z * g.kb_per_split;
+    const int nkb = min(g.kb_per_split, nkb_total - kb0);
+
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 128);
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < dn::STAGES; ++s) tc::mbar_init(&mbar_free[s], 1);
+        tc::mbar_init(&mbar_done, 1);
+        tc::mbar_fence_init();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+
+    constexpr bool A_ASYNC = is_bf16<TA>::value, B_ASYNC = is_bf16<TB>::value;
+    constexpr uint32_t idesc = tc::make_idesc_bf16(dn::BM, dn::BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    constexpr uint32_t A_LBO = A_MN ? 128u : dn::SLAB_K, A_SBO = A_MN ? dn::SLAB_MN : 128u, A_KSTEP = A_MN ? 256u : 2u * dn::SLAB_K;
+    constexpr uint32_t B_LBO = B_MN ? 128u : dn::SLAB_K, B_SBO = B_MN ? dn::SLAB_MN : 128u, B_KSTEP = B_MN ? 256u : 2u * dn::SLAB_K;
+    const uint32_t sm_base = tc::smem_u32(sm);
+
+    // register-staged path (fp32 sources, converted on the fly): one K block ahead
+    Stager<float, A_MN> sa;
+    Stager<float, B_MN> sb;
+    auto fetch_regs = [&](int kb) {
+        const int64_t k0 = (int64_t)(kb0 + kb) * dn::BK;
+        if constexpr (!A_ASYNC) {
+            if (A_MN) sa.load((const float*)g.A, g.lda, k0, m0, g.K, g.M, tid);
+            else if (k0 < g.k_split) sa.load((const float*)g.A, g.lda, m0, k0, g.M, g.k_split, tid);
+            else sa.load((const float*)g.A2, g.lda2, m0, k0 - g.k_split, g.M, g.K - g.k_split, tid);
+        }
+        if constexpr (!B_ASYNC) {
+            if (B_MN) sb.load((const float*)g.B, g.ldb, k0, n0, g.K, g.N, tid);
+            else      sb.load((const float*)g.B, g.ldb, n0, k0, g.N, g.K, tid);
+        }
+    };
+    // cp.async path (bf16 sources): STAGES-1 K blocks ahead
+    auto issue_async = [&](int kb) {
+        const int64_t k0 = (int64_t)(kb0 + kb) * dn::BK;
+        const uint32_t st = sm_base + (kb % dn::STAGES) * dn::STAGE_BYTES;
+        if constexpr (A_ASYNC) {
+            if (A_MN) stage_async<true>((const bf16*)g.A, g.lda, k0, m0, g.K, g.M, st, tid);
+            else if (k0 < g.k_split) stage_async<false>((const bf16*)g.A, g.lda, m0, k0, g.M, g.k_split, st, tid);
+            else stage_async<false>((const bf16*)g.A2, g.lda2, m0, k0 - g.k_split, g.M, g.K - g.k_split, st, tid);
+        }
+        if constexpr (B_ASYNC) {
+            if (B_MN) stage_async<true>((const bf16*)g.B, g.ldb, k0, n0, g.K, g.N, st + dn::OP_BYTES, tid);
+            else      stage_async<false>((const bf16*)g.B, g.ldb, n0, k0, g.N, g.K, st + dn::OP_BYTES, tid);
+        }
+    };
+
+    if constexpr (A_ASYNC || B_ASYNC) {
+#pragma unroll
+        for (int p = 0; p < dn::STAGES - 1; ++p) {
+            if (p < nkb) issue_async(p);
+            cp_async_commit();
+        }
+    }
+    if constexpr (!A_ASYNC || !B_ASYNC) { if (nkb > 0) fetch_regs(0); }
+    for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % dn::STAGES;
+        // stage (kb-1)%STAGES is re-filled below with block kb+STAGES-1: its previous reader is MMA(kb-1)
+        if constexpr (A_ASYNC || B_ASYNC) {
+            if (kb >= 1) tc::mbar_wait(&mbar_free[(kb - 1) % dn::STAGES], (uint32_t)(((kb - 1) / dn::STAGES) & 1));
+        } else {
+            if (kb >= dn::STAGES) tc::mbar_wait(&mbar_free[s], (uint32_t)((kb / dn::STAGES - 1) & 1));
+        }
+        if constexpr (A_ASYNC || B_ASYNC) {
+            if (kb + dn::STAGES - 1 < nkb) issue_async(kb + dn::STAGES - 1);
+            cp_async_commit();
+        }
+        if constexpr (!A_ASYNC || !B_ASYNC) {
+            uint8_t* stA = sm + s * dn::STAGE_BYTES;
+            if constexpr (!A_ASYNC) sa.store(stA, tid);
+            if constexpr (!B_ASYNC) sb.store(stA + dn::OP_BYTES, tid);
+            if (kb + 1 < nkb) fetch_regs(kb + 1);
+        }
+        if constexpr (A_ASYNC || B_ASYNC) cp_async_wait<dn::STAGES - 1>();
+        tc::fence_async_smem();
+        tc::fence_before_sync();
+        __syncthreads();
+        if (warp == 0) {
+            if (tc::elect_one()) {
+                tc::fence_after_sync();
+                const tc::Desc dA = tc::make_desc2(sm_base + s * dn::STAGE_BYTES, A_LBO, A_SBO);
+                const tc::Desc dB = tc::make_desc2(sm_base + s * dn::STAGE_BYTES + dn::OP_BYTES, B_LBO, B_SBO);
+#pragma unroll
+                for (int ks = 0; ks < dn::BK / 16; ++ks)
+                    tc::mma_bf16(tmem, dA.adv(ks * A_KSTEP).u64(), dB.adv(ks * B_KSTEP).u64(), idesc, (kb | ks) != 0);
+                tc::mma_commit(kb + 1 == nkb ? &mbar_done : &mbar_free[s]);
+            }
+            __syncwarp();
+        }
+    }
+
+    // ---- epilogue: warp w owns TMEM lanes 32*(w%4).. (+32 rows) and columns 64*(w/4).. (+64) ----
+    if (nkb > 0) {
+        tc::mbar_wait(&mbar_done, 0);
+        tc::fence_after_sync();
+    }
+    const int lg = warp & 3, ch = warp >> 2;
+    float* tr = reinterpret_cast<float*>(sm) + warp * 1024;       // 32 x 32 fp32, float4 slots XOR-swizzled by row
+    const bool partial = g.partial != nullptr;
+    float* outp = partial ? g.partial + (size_t)blockIdx.z * g.M * g.N : nullptr;
+#pragma unroll 1
+    for (int slab = 0; slab < 2; ++slab) {
+        const int c0 = ch * 64 + slab * 32;
+        float v[32];
+        if (nkb > 0) {
+            tc::tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + c0, v);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) v[c] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(tr + lane * 32 + 4 * (j ^ (lane & 7))) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        const int j = lane & 7;
+        const int64_t col = n0 + c0 + 4 * j;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int R = it * 4 + (lane >> 3);
+            const int64_t row = m0 + lg * 32 + R;
+            float4 x = *reinterpret_cast<const float4*>(tr + R * 32 + 4 * (j ^ (R & 7)));
+            if (row < g.M && col < g.N) {
+                if (partial) {
+                    *reinterpret_cast<float4*>(outp + row * g.N + col) = x;
+                } else {
+                    if (g.bias) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + col));
+                        x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+                    }
+                    if (g.residual) {
+                        const float4 r = __ldg(reinterpret_cast<const float4*>(g.residual + row * g.ldr + col));
+                        x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
+                    }
+                    if (g.c_bf16) {
+                        uint2 o;
+                        o.x = tc::pack_bf16(x.x, x.y); o.y = tc::pack_bf16(x.z, x.w);
+                        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(g.C) + row * g.ldc + col) = o;
+                    } else {
+                        float* cp = reinterpret_cast<float*>(g.C) + row * g.ldc + col;
+                        if (g.accumulate) {
+                            const float4 c = *reinterpret_cast<const float4*>(cp);
+                            x.x += c.x; x.y += c.y; x.z += c.z; x.w += c.w;
+                        }
+                        *reinterpret_cast<float4*>(cp) = x;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 128);
+}
+
+// fixed-order sum of the split-K partials (+ bias / accumulate): deterministic weight gradients
+__global__ void __launch_bounds__(256)
+gemm_splitk_reduce_kernel(const float* __restrict__ part, int splits, int64_t M, int64_t N, const float* __restrict__ bias,
+                          float* __restrict__ C, int64_t ldc, int accumulate) {
+    const int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total4 = M * N / 4;
+    if (i4 >= total4) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int z = 0; z < splits; ++z) {
+        const float4 p = __ldg(reinterpret_cast<const float4*>(part + (size_t)z * M * N) + i4);
+        acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+    }
+    const int64_t row = (i4 * 4) / N, col = (i4 * 4) % N;
+    if (bias) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col));
+        acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+    }
+    float* cp = C + row * ldc + col;
+    if (accumulate) {
+        const float4 c = *reinterpret_cast<const float4*>(cp);
+        acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += c.w;
+    }
+    *reinterpret_cast<float4*>(cp) = acc;
+}
+
+static int pick_splits(int64_t M, int64_t N, int64_t K) {
+    const int64_t tiles = ((M + dn::BM - 1) / dn::BM) * ((N + dn::BN - 1) / dn::BN);
+    const int64_t nkb = (K + dn::BK - 1) / dn::BK;
+    if (tiles >= kNumSMs || nkb < 8) return 1;
+    int64_t s = (2 * kNumSMs + tiles - 1) / tiles;
+    s = std::min<int64_t>(s, nkb / 4);
+    return (int)std::max<int64_t>(s, 1);
+}
+
+template <typename TA, typename TB, bool A_MN, bool B_MN>
+static int launch_gemm(const GemmArgs& g, int splits, cudaStream_t st) {
+    static bool attr_done = false;
+    auto kern = gemm_tc_kernel<TA, TB, A_MN, B_MN>;
+    if (!attr_done) {
+        GAOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dn::SMEM_BYTES));
+        attr_done = true;
+    }
+    dim3 grid((unsigned)((g.N + dn::BN - 1) / dn::BN), (unsigned)((g.M + dn::BM - 1) / dn::BM), (unsigned)splits);
+    kern<<<grid, dn::THREADS, dn::SMEM_BYTES, st>>>(g);
+    GAOT_LAUNCH_CHECK();
+    return GAOT_OK;
+}
+
+// dtype codes of the C ABI: 0 = float32, 1 = bfloat16
+static int run_gemm(GemmArgs g, int a_dtype, int b_dtype, bool a_mn, bool b_mn, void* ws, size_t ws_bytes, cudaStream_t st,
+                    const char* timer_name) {
+    GAOT_CHECK_ARG(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem");
+    GAOT_CHECK_ARG(g.N % 4 == 0 && g.ldc % 4 == 0, "gemm: N and ldc must be multiples of 4");
+    const int64_t a_al = a_dtype ? 8 : 4, b_al = b_dtype ? 8 : 4;
+    if (g.lda % a_al || g.ldb % b_al || (g.A2 && g.lda2 % a_al) || (a_mn ? g.M : g.K) % a_al || (b_mn ? g.N : g.K) % b_al ||
+        (g.A2 && (g.k_split % dn::BK || a_mn))) {
+        set_error("gemm: operand rows must be 16-byte aligned (contiguous extents multiples of %d/%d elements)", (int)a_al, (int)b_al);
+        return GAOT_ERR_UNSUPPORTED;
+    }
+    if (!g.A2) g.k_split = g.K;
+    const int nkb = (int)((g.K + dn::BK - 1) / dn::BK);
+    int splits = (g.c_bf16 || g.residual) ? 1 : pick_splits(g.M, g.N, g.K);
+    g.kb_per_split = (nkb + splits - 1) / splits;
+    splits = (nkb + g.kb_per_split - 1) / g.kb_per_split;
+    g.partial = nullptr;
+    if (splits > 1) {
+        const size_t need = (size_t)splits * g.M * g.N * sizeof(float);
+        if (ws_bytes < need || !ws) { set_error("gemm: workspace too small (%zu < %zu)", ws_bytes, need); return GAOT_ERR_WORKSPACE; }
+        g.partial = (float*)ws;
+    }
+    GAOT_TIME_KERNEL(timer_name, st, 2.0 * (double)g.M * (double)g.N * (double)g.K);
+    int rc;
+    const int sel = (a_dtype ? 8 : 0) | (b_dtype ? 4 : 0) | (a_mn ? 2 : 0) | (b_mn ? 1 : 0);
+    switch (sel) {
+        case 0:  rc = launch_gemm<float, float, false, false>(g, splits, st); break;
+        case 1:  rc = launch_gemm<float, float, false, true>(g, splits, st); break;
+        case 3:  rc = launch_gemm<float, float, true, true>(g, splits, st); break;
+        case 4:  rc = launch_gemm<float, bf16, false, false>(g, splits, st); break;
+        case 5:  rc = launch_gemm<float, bf16, false, true>(g, splits, st); break;
+        case 12: rc = launch_gemm<bf16, bf16, false, false>(g, splits, st); break;
+        case 13: rc = launch_gemm<bf16, bf16, false, true>(g, splits, st); break;
+        case 15: rc = launch_gemm<bf16, bf16, true, true>(g, splits, st); break;
+        case 11: rc = launch_gemm<bf16, float, true, true>(g, splits, st); break;
+        case 7:  rc = launch_gemm<float, bf16, true, true>(g, splits, st); break;
+        default: set_error("gemm: operand combination %d not instantiated", sel); return GAOT_ERR_UNSUPPORTED;
+    }
+    if (rc != GAOT_OK) return rc;
+    if (splits > 1) {
+        const int64_t total4 = g.M * g.N / 4;
+        gemm_splitk_reduce_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(g.partial, splits, g.M, g.N, g.bias, (float*)g.C, g.ldc, g.accumulate);
+        GAOT_LAUNCH_CHECK();
+    }
+    return GAOT_OK;
+}
+
+}  // namespace gaot
+
+using namespace gaot;
+
+extern "C" {
+
+size_t gaot_linear_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+    // upper bound over the three products of one layer (split-K partials of the largest split count)
+    auto need = [](int64_t m, int64_t n, int64_t k) { return (size_t)pick_splits(m, n, k) * m * n * sizeof(float); };
+    size_t b = std::max(need(M, N, K), std::max(need(M, K, N), need(N, K, M)));
+    return align_up(b + 256);
+}
+
+int gaot_linear_forward(const void* x, int x_dtype, int64_t ldx, const void* x2, int64_t ldx2, int64_t k_split,
+                        const void* w, int w_dtype, int64_t M, int64_t N, int64_t K,
+                        const float* bias, const float* residual, int64_t ldr,
+                        void* y, int y_dtype, int64_t ldy, void* ws, size_t ws_bytes, void* stream) {
+    GAOT_CHECK_ARG(x && w && y, "linear_forward: null pointer");
+    GemmArgs g{};
+    g.A = x; g.lda = ldx; g.A2 = x2; g.lda2 = ldx2; g.k_split = x2 ? k_split : K;
+    g.B = w; g.ldb = K; g.M = M; g.N = N; g.K = K;
+    g.bias = bias; g.residual = residual; g.ldr = ldr; g.C = y; g.ldc = ldy; g.c_bf16 = y_dtype; g.accumulate = 0;
+    return run_gemm(g, x_dtype, w_dtype, false, false, ws, ws_bytes, (cudaStream_t)stream, "linear_fwd");
+}
+
+int gaot_linear_backward_input(const void* dy, int dy_dtype, int64_t lddy, const void* w, int w_dtype,
+                               int64_t M, int64_t N, int64_t K, const float* residual, int64_t ldr,
+                               void* dx, int dx_dtype, int64_t lddx, int accumulate,
+                               void* ws, size_t ws_bytes, void* stream) {
+    GAOT_CHECK_ARG(dy && w && dx, "linear_backward_input: null pointer");
+    GemmArgs g{};
+    g.A = dy; g.lda = lddy; g.B = w; g.ldb = K;
+    g.M = M; g.N = K; g.K = N;                                    // dx[M,K] = dy[M,N] * W[N,K], contraction over N
+    g.residual = residual; g.ldr = ldr; g.C = dx; g.ldc = lddx; g.c_bf16 = dx_dtype; g.accumulate = accumulate;
+    return run_gemm(g, dy_dtype, w_dtype, false, true, ws, ws_bytes, (cudaStream_t)stream, "linear_bwd_x");
+}
+
+int gaot_linear_backward_weight(const void* dy, int dy_dtype, int64_t lddy, const void* x, int x_dtype, int64_t ldx,
+                                int64_t M, int64_t N, int64_t K, float* dw, int64_t lddw, int accumulate,
+                                void* ws, size_t ws_bytes, void* stream) {
+    GAOT_CHECK_ARG(dy && x && dw, "linear_backward_weight: null pointer");
+    GemmArgs g{};
+    g.A = dy; g.lda = lddy; g.B = x; g.ldb = ldx;
+    g.M = N; g.N = K; g.K = M;                                    // dW[N,K] = dy^T[N,M] * x[M,K], contraction over M
+    g.C = dw; g.ldc = lddw; g.c_bf16 = 0; g.accumulate = accumulate;
+    return run_gemm(g, dy_dtype, x_dtype, true, true, ws, ws_bytes, (cudaStream_t)stream, "linear_bwd_w");
+}
+
+}  // extern "C"

@@ -3,8 +3,9 @@
 Config dataclasses keep the reference's field names/defaults; modules keep parameter names
 (`attn.{q,k,v,o}_proj.weight`, `attn.rotary_emb.freqs`, `ffn.{w1,w2,w3}.weight`,
 `attn_norm.weight`, `ffn_norm.weight`, `skip_proj.*`).  The attention core (RoPE + softmax(QK^T)V,
-reference :110-128) is the tcgen05/TMEM flash kernel of this package; projections, SwiGLU FFN
-and RMSNorm stay torch/cuBLAS.
+reference :110-128) is the tcgen05/TMEM flash kernel of this package; the projections, the SwiGLU
+GEMMs and skip_proj run on the tcgen05 dense kernel (csrc/dense.cu) with the residual adds fused
+into the GEMM epilogues.
 """
 from dataclasses import dataclass, field, fields, is_dataclass
 from typing import Optional
@@ -13,7 +14,11 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .. import ops
+from .. import ops, tblock
+
+# True: a TransformerBlock is ONE autograd node running only this library's kernels with bf16 hand-offs (tblock.py);
+# False: module-by-module path (tcgen05 GEMMs and attention, torch RMSNorm / SiLU / adds in fp32)
+FUSED_BLOCK = True
 
 
 @dataclass
@@ -56,6 +61,17 @@ def _cfg_dict(obj) -> dict:
     return dict(obj)
 
 
+def _lin(mod: nn.Linear, x, residual=None, x2=None):
+    """nn.Linear forward on the tcgen05 dense kernel (parameters stay in the nn.Linear, so state_dict keys match)."""
+    if x.is_cuda and ops.linear_supported(mod.in_features, mod.out_features) and (x2 is None or x.shape[-1] % 64 == 0):
+        return ops.linear(x, mod.weight, mod.bias, residual=residual, x2=x2)
+    if not x.is_cuda:
+        raise RuntimeError("gaot_3d_b200: the B200 hot path has no CPU fallback; got a CPU tensor")
+    # shapes outside the kernel envelope (rows not 16-byte aligned): node-level torch path, SURVEY 8f
+    y = mod(x if x2 is None else torch.cat([x, x2], dim=-1))
+    return y if residual is None else y + residual
+
+
 class RotaryEmbedding(nn.Module):
     """Carrier of the `freqs` state_dict entry of rotary_embedding_torch.RotaryEmbedding(dim)
     (theta 10000, non-trainable nn.Parameter); the rotation itself is fused into the attention
@@ -88,14 +104,17 @@ class GroupQueryFlashAttention(nn.Module):
         if positional_embedding == "rope":
             self.rotary_emb = RotaryEmbedding(dim=self.head_dim)
 
-    def forward(self, x, condition: Optional[float] = None, relative_positions: Optional[torch.Tensor] = None):
+    def forward(self, x, condition: Optional[float] = None, relative_positions: Optional[torch.Tensor] = None,
+                residual: Optional[torch.Tensor] = None):
+        """`residual` (extension): added to the o_proj output inside the GEMM epilogue (x + attn(x))."""
         lead = x.shape[:-2]
         x3 = x.reshape(-1, x.shape[-2], x.shape[-1])
-        q, k, v = self.q_proj(x3), self.k_proj(x3), self.v_proj(x3)
+        q, k, v = _lin(self.q_proj, x3), _lin(self.k_proj, x3), _lin(self.v_proj, x3)
         dp = self.atten_dropout if self.training else 0.0          # reference attn.py:122-126
         freqs = self.rotary_emb.freqs if relative_positions is not None else None
         o = ops.attention(q, k, v, self.num_heads, self.num_kv_heads, rope_freqs=freqs, dropout_p=dp)
-        return self.o_proj(o.to(x.dtype)).reshape(*lead, x.shape[-2], -1)
+        res3 = None if residual is None else residual.reshape(x3.shape[0], x3.shape[1], -1)
+        return _lin(self.o_proj, o, residual=res3).reshape(*lead, x.shape[-2], -1)
 
     @classmethod
     def from_config(cls, input_size: int, output_size: int, config: AttentionConfig):
@@ -116,8 +135,8 @@ class FFN(nn.Module):
             raise NotImplementedError("time-conditional norm is unused by the 3-D static path")
         self.correction = None
 
-    def forward(self, x, condition: Optional[float] = None):
-        return self.w2(F.silu(self.w1(x)) * self.w3(x))
+    def forward(self, x, condition: Optional[float] = None, residual: Optional[torch.Tensor] = None):
+        return _lin(self.w2, F.silu(_lin(self.w1, x)) * _lin(self.w3, x), residual=residual)
 
     @classmethod
     def from_config(cls, input_size: int, output_size: int, config: FFNConfig):
@@ -151,12 +170,32 @@ class TransformerBlock(nn.Module):
             self.skip_proj = nn.Linear(input_size + output_size, input_size)
 
     def forward(self, x, condition=None, relative_positions=None, skip=None):
+        if self._fused_ok(x, condition):
+            use_skip = self.skip_connection and skip is not None
+            a, f = self.attn, self.ffn
+            return tblock.transformer_block(
+                x, skip if use_skip else None, num_heads=a.num_heads, num_kv_heads=a.num_kv_heads, eps=self.attn_norm.eps,
+                rope_freqs=a.rotary_emb.freqs if (relative_positions is not None and hasattr(a, "rotary_emb")) else None,
+                dropout_p=a.atten_dropout if self.training else 0.0,
+                skip_w=self.skip_proj.weight if use_skip else None, skip_b=self.skip_proj.bias if use_skip else None,
+                attn_norm_w=self.attn_norm.weight, wq=a.q_proj.weight, wk=a.k_proj.weight, wv=a.v_proj.weight,
+                wo=a.o_proj.weight, ffn_norm_w=self.ffn_norm.weight, w1=f.w1.weight, w2=f.w2.weight, w3=f.w3.weight)
         if self.skip_connection and skip is not None:
-            x = self.skip_proj(torch.cat([x, skip], dim=-1))
+            x = _lin(self.skip_proj, x, x2=skip)                  # Linear over cat[x, skip], read in place
         h = x if self.attn_norm is None else self.attn_norm(x)
-        h = x + self.attn(h, condition=condition, relative_positions=relative_positions)
+        h = self.attn(h, condition=condition, relative_positions=relative_positions, residual=x)   # x + attn(h)
         h = h if self.ffn_norm is None else self.ffn_norm(h)      # reference quirk: residual taken after the norm
-        return h + self.ffn(h, condition=condition)
+        return self.ffn(h, condition=condition, residual=h)       # h + ffn(h)
+
+    def _fused_ok(self, x, condition) -> bool:
+        """One-autograd-node path (tblock.py): both norms present, square block, shapes inside the kernel envelope."""
+        a, f = self.attn, self.ffn
+        hid = a.q_proj.in_features
+        return (FUSED_BLOCK and x.is_cuda and x.dtype == torch.float32 and self.attn_norm is not None and self.ffn_norm is not None
+                and a.q_proj.out_features == hid and a.o_proj.out_features == hid and f.w2.out_features == hid
+                and f.w1.in_features == hid and self.attn_norm.eps == self.ffn_norm.eps
+                and (not self.skip_connection or self.skip_proj.in_features == 2 * hid)
+                and tblock.block_supported(hid, f.w1.out_features, a.num_heads, a.num_kv_heads))
 
     @classmethod
     def from_config(cls, input_size: int, output_size: int, skip_connection: bool = False,
@@ -186,7 +225,7 @@ class Transformer(nn.Module):
         self.decoder_layers = nn.ModuleList(mk(True) for _ in range(nl // 2))
 
     def forward(self, x, condition=None, relative_positions=None):
-        x = self.input_proj(x)
+        x = x if isinstance(self.input_proj, nn.Identity) else _lin(self.input_proj, x)
         skips = []
         for layer in self.encoder_layers:
             x = layer(x, condition=condition, relative_positions=relative_positions)
@@ -196,4 +235,4 @@ class Transformer(nn.Module):
         for layer in self.decoder_layers:
             skip = skips.pop() if self.use_long_range_skip else None
             x = layer(x, condition=condition, relative_positions=relative_positions, skip=skip)
-        return self.output_proj(x)
+        return x if isinstance(self.output_proj, nn.Identity) else _lin(self.output_proj, x)

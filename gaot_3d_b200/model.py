@@ -8,7 +8,7 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
-from .layers.attn import Transformer, TransformerConfig
+from .layers.attn import Transformer, TransformerConfig, _lin
 from .layers.magno import MAGNOConfig, MAGNODecoder, MAGNOEncoder
 
 
@@ -70,7 +70,7 @@ class GAOT3D(nn.Module):
         assert D % P == 0 and H % P == 0 and W % P == 0, "Dimensions must be divisible by patch size"
         nd, nh, nw = D // P, H // P, W // P
         x = rndata.view(B, nd, P, nh, P, nw, P, C).permute(0, 1, 3, 5, 2, 4, 6, 7).contiguous()
-        x = self.patch_linear(x.view(B, nd * nh * nw, P * P * P * C))
+        x = _lin(self.patch_linear, x.view(B, nd * nh * nw, P * P * P * C))
         pos = self.positions.to(x.device)
         relative_positions = None
         if self.positional_embedding_name == "absolute":

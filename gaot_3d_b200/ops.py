@@ -347,6 +347,132 @@ def zscore_(feat: torch.Tensor) -> torch.Tensor:
     return feat
 
 
+# ----------------------------------------------------------------------------- dense layers (nn.Linear)
+_DT = {torch.float32: 0, torch.bfloat16: 1}
+
+
+def linear_supported(in_features: int, out_features: int) -> bool:
+    """Shapes the tcgen05 GEMM takes (16-byte aligned rows for fp32 and bf16 operands)."""
+    return in_features % 8 == 0 and out_features % 8 == 0 and in_features >= 16 and out_features >= 16
+
+
+def _rows(t: torch.Tensor) -> torch.Tensor:
+    t = t.reshape(-1, t.shape[-1])
+    if t.dtype not in _DT:
+        t = t.to(torch.float32)
+    return t if t.stride(1) == 1 and t.stride(0) % 8 == 0 and t.data_ptr() % 16 == 0 else t.contiguous()
+
+
+def _lin_ws(lib, M, N, K, dev):
+    wsb = lib.gaot_linear_workspace_bytes(M, N, K)
+    return _ws(wsb, dev), wsb
+
+
+def _linear_fwd_raw(x, x2, w, bias, residual, out_dtype=torch.float32):
+    lib = _lib_()
+    M, K1 = x.shape
+    K = K1 + (0 if x2 is None else x2.shape[1])
+    N = w.shape[0]
+    dev = x.device
+    y = torch.empty(M, N, dtype=out_dtype, device=dev)
+    if M == 0:
+        return y
+    ws, wsb = _lin_ws(lib, M, N, K, dev)
+    with torch.cuda.device(dev):
+        check(lib.gaot_linear_forward(_p(x), _DT[x.dtype], x.stride(0), _p(x2), 0 if x2 is None else x2.stride(0), K1,
+                                      _p(w), _DT[w.dtype], M, N, K, _p(bias), _p(residual),
+                                      0 if residual is None else residual.stride(0), _p(y), _DT[out_dtype], y.stride(0),
+                                      _p(ws), wsb, _stream(dev)), "linear_forward")
+    return y
+
+
+def _linear_bwd_x_raw(dy, w, out_dtype=torch.float32, residual=None):
+    lib = _lib_()
+    M, N = dy.shape
+    K = w.shape[1]
+    dev = dy.device
+    dx = torch.empty(M, K, dtype=out_dtype, device=dev)
+    if M == 0:
+        return dx
+    ws, wsb = _lin_ws(lib, M, N, K, dev)
+    with torch.cuda.device(dev):
+        check(lib.gaot_linear_backward_input(_p(dy), _DT[dy.dtype], dy.stride(0), _p(w), _DT[w.dtype], M, N, K,
+                                             _p(residual), 0 if residual is None else residual.stride(0),
+                                             _p(dx), _DT[out_dtype], dx.stride(0), 0, _p(ws), wsb, _stream(dev)),
+              "linear_backward_input")
+    return dx
+
+
+def _linear_bwd_w_raw(dy, x, dw, accumulate=False):
+    """dw[N, K'] (a column slice of the weight gradient, row stride dw.stride(0)) = dy^T x."""
+    lib = _lib_()
+    M, N = dy.shape
+    K = x.shape[1]
+    dev = dy.device
+    if M == 0:
+        if not accumulate:
+            dw.zero_()
+        return dw
+    ws, wsb = _lin_ws(lib, M, N, K, dev)
+    with torch.cuda.device(dev):
+        check(lib.gaot_linear_backward_weight(_p(dy), _DT[dy.dtype], dy.stride(0), _p(x), _DT[x.dtype], x.stride(0),
+                                              M, N, K, _p(dw), dw.stride(0), 1 if accumulate else 0, _p(ws), wsb,
+                                              _stream(dev)), "linear_backward_weight")
+    return dw
+
+
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, x2, weight, bias, residual):
+        shape = x.shape
+        xr = _rows(x.detach())
+        x2r = None if x2 is None else _rows(x2.detach())
+        w = weight.detach().to(torch.float32).contiguous()
+        b = None if bias is None else bias.detach().to(torch.float32).contiguous()
+        r = None if residual is None else _rows(residual.detach()).to(torch.float32)
+        y = _linear_fwd_raw(xr, x2r, w, b, r)
+        ctx.save_for_backward(xr, x2r, w)
+        ctx.meta = (shape, None if x2 is None else x2.shape, None if residual is None else residual.shape, bias is not None)
+        return y.view(*shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        xr, x2r, w = ctx.saved_tensors
+        shape, shape2, rshape, has_bias = ctx.meta
+        dyr = _rows(dy)
+        need_x, need_x2, need_w, need_b, need_r = ctx.needs_input_grad
+        dx = dx2 = dw = db = dr = None
+        if need_x or (need_x2 and x2r is not None):
+            dfull = _linear_bwd_x_raw(dyr, w)
+            k1 = xr.shape[1]
+            if need_x:
+                dx = dfull[:, :k1].reshape(shape) if x2r is None else dfull[:, :k1].view(*shape[:-1], k1)
+            if need_x2 and x2r is not None:
+                dx2 = dfull[:, k1:].view(*shape2[:-1], shape2[-1])
+        if need_w:
+            dw = torch.empty_like(w)
+            k1 = xr.shape[1]
+            _linear_bwd_w_raw(dyr, xr, dw[:, :k1] if x2r is not None else dw)
+            if x2r is not None:
+                _linear_bwd_w_raw(dyr, x2r, dw[:, k1:])
+        if need_b and has_bias:
+            db = dyr.sum(0)
+        if need_r and rshape is not None:
+            dr = dy.reshape(rshape)
+        return dx, dx2, dw, db, dr
+
+
+def linear(x, weight, bias=None, residual=None, x2=None):
+    """y = [x | x2] weight^T (+ bias) (+ residual) on tcgen05 (bf16 operands, fp32 accumulate) -- the nn.Linear
+    of the latent transformer (reference attn.py:104-106,:129,:163,:223; gaot_3d.py:205).  `x2` is the second
+    half of a concatenated input (skip_proj over cat[x, skip]) read in place."""
+    _need_cuda(x, weight, bias, residual, x2)
+    k1 = x.shape[-1]
+    if not linear_supported(weight.shape[1], weight.shape[0]) or (x2 is not None and k1 % 64 != 0):
+        raise NotImplementedError(f"linear: shape [{weight.shape[0]}, {weight.shape[1]}] outside the tensor-core kernel envelope")
+    return _LinearFn.apply(x, x2, weight, bias, residual)
+
+
 # ----------------------------------------------------------------------------- attention
 class _AttnFn(torch.autograd.Function):
     @staticmethod

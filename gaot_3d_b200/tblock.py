@@ -1,0 +1,203 @@
+"""One autograd node per latent TransformerBlock (reference src/model/layers/attn.py:205-230).
+
+    [x = skip_proj(cat[x, skip])]; h = x + o_proj(attn(RMSNorm(x))); h = RMSNorm(h); out = h + w2(silu(w1 h) * w3 h)
+
+The forward is 11 launches of this library's kernels, the backward 19; no torch op runs in between.  The residual
+stream (x, h, normalised h, out and their gradients) stays fp32; everything that only feeds a GEMM or the
+attention core is handed over in bf16, written by the producing kernel in the layout the consumer reads:
+
+  rmsnorm_fwd -> h1 bf16 -> [Wq;Wk;Wv] GEMM -> qkv bf16 -> pack (+RoPE) -> tcgen05 attention -> o bf16
+  -> o_proj GEMM (+x in the epilogue) -> h fp32 -> rmsnorm_fwd -> h2 fp32 + bf16 -> [W1;W3] GEMM -> gu bf16
+  -> swiglu -> a bf16 -> w2 GEMM (+h2 in the epilogue) -> out fp32
+
+Weights are cast to bf16 once per call (they change every optimizer step); q/k/v and w1/w3 are cast into one
+concatenated operand so that each pair of projections is one GEMM.  Weight gradients come out of split-K GEMMs
+with a fixed-order reduction, so the whole block is bit-reproducible except for the attention dQ reductions.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import ops
+from .ops import _lib_, _p, _stream, _ws, check, _linear_fwd_raw, _linear_bwd_x_raw, _linear_bwd_w_raw
+
+BF16 = torch.bfloat16
+
+
+def _cast_into(src: torch.Tensor, dst: torch.Tensor) -> None:
+    """fp32 parameter -> bf16 operand (dst is a contiguous row slice of the concatenated operand)."""
+    lib = _lib_()
+    s = src.detach()
+    if s.dtype != torch.float32 or not s.is_contiguous():
+        s = s.to(torch.float32).contiguous()
+    check(lib.gaot_cast_bf16(_p(s), _p(dst), s.numel(), _stream(s.device)), "cast_bf16")
+
+
+def _cast(src: torch.Tensor) -> torch.Tensor:
+    dst = torch.empty(src.shape, dtype=BF16, device=src.device)
+    _cast_into(src, dst)
+    return dst
+
+
+def _rmsnorm_fwd(x, w, eps, want_f32: bool):
+    lib = _lib_()
+    M, H = x.shape
+    dev = x.device
+    yb = torch.empty(M, H, dtype=BF16, device=dev)
+    yf = torch.empty(M, H, dtype=torch.float32, device=dev) if want_f32 else None
+    rstd = torch.empty(M, dtype=torch.float32, device=dev)
+    check(lib.gaot_rmsnorm_forward(_p(x), _p(w), M, H, float(eps), _p(yb), _p(yf), _p(rstd), _stream(dev)), "rmsnorm_forward")
+    return yb, yf, rstd
+
+
+def _rmsnorm_bwd(dy, x, rstd, w, dres):
+    lib = _lib_()
+    M, H = x.shape
+    dev = x.device
+    dx = torch.empty(M, H, dtype=torch.float32, device=dev)
+    dw = torch.empty(H, dtype=torch.float32, device=dev)
+    wsb = lib.gaot_rmsnorm_backward_workspace_bytes(H)
+    ws = _ws(wsb, dev)
+    check(lib.gaot_rmsnorm_backward(_p(dy), _p(x), _p(rstd), _p(w), _p(dres), M, H, _p(dx), _p(dw), _p(ws), wsb,
+                                    _stream(dev)), "rmsnorm_backward")
+    return dx, dw
+
+
+def _colsum(x):
+    lib = _lib_()
+    M, N = x.shape
+    out = torch.empty(N, dtype=torch.float32, device=x.device)
+    wsb = lib.gaot_colsum_workspace_bytes(M, N)
+    ws = _ws(wsb, x.device)
+    check(lib.gaot_colsum(_p(x), M, N, _p(out), _p(ws), wsb, _stream(x.device)), "colsum")
+    return out
+
+
+def block_supported(hidden: int, ffn_hidden: int, num_heads: int, num_kv_heads: int) -> bool:
+    d = hidden // max(num_heads, 1)
+    return (hidden % 128 == 0 and 128 <= hidden <= 1024 and d in (32, 64) and num_heads * d == hidden
+            and num_heads % num_kv_heads == 0 and ffn_hidden % 64 == 0)
+
+
+class _BlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, skip, cfg, skip_w, skip_b, n1_w, wq, wk, wv, wo, n2_w, w1, w2, w3):
+        lib = _lib_()
+        H, Hkv, eps, freqs, p_drop, seed = cfg
+        shape = x.shape
+        S, Hd = shape[-2], shape[-1]
+        B = x.numel() // (S * Hd)
+        M = B * S
+        d = Hd // H
+        dev = x.device
+        f32 = lambda t: t.detach().to(torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            x2d = f32(x).view(M, Hd)
+            if skip is not None:
+                s2d = f32(skip).view(M, -1)
+                wsk = _cast(skip_w)
+                x_in = _linear_fwd_raw(x2d, s2d, wsk, f32(skip_b) if skip_b is not None else None, None)
+            else:
+                s2d = wsk = None
+                x_in = x2d
+            n1, n2 = f32(n1_w), f32(n2_w)
+            h1, _, rstd1 = _rmsnorm_fwd(x_in, n1, eps, False)
+            nq, nkv = H * d, Hkv * d
+            wqkv = torch.empty(nq + 2 * nkv, Hd, dtype=BF16, device=dev)
+            _cast_into(wq, wqkv[:nq]); _cast_into(wk, wqkv[nq:nq + nkv]); _cast_into(wv, wqkv[nq + nkv:])
+            qkv = _linear_fwd_raw(h1, None, wqkv, None, None, BF16)
+            packed = torch.empty(lib.gaot_attn_packed_bytes(B, S, H, Hkv, d), dtype=torch.uint8, device=dev)
+            o = torch.empty(M, nq, dtype=BF16, device=dev)
+            lse = torch.empty(B, H, S, dtype=torch.float32, device=dev)
+            fr = None if freqs is None else f32(freqs)
+            with ops._timed("attn_fwd", dev):
+                check(lib.gaot_attn_fused_forward(_p(qkv), qkv.stride(0), B, S, H, Hkv, d, _p(fr), float(p_drop), int(seed),
+                                                  _p(packed), _p(o), _p(lse), _stream(dev)), "attn_fused_forward")
+            del qkv
+            wob = _cast(wo)
+            h = _linear_fwd_raw(o, None, wob, None, x_in)                       # x + attn(norm(x))
+            h2b, h2, rstd2 = _rmsnorm_fwd(h, n2, eps, True)
+            F = w1.shape[0]
+            w13 = torch.empty(2 * F, Hd, dtype=BF16, device=dev)
+            _cast_into(w1, w13[:F]); _cast_into(w3, w13[F:])
+            gu = _linear_fwd_raw(h2b, None, w13, None, None, BF16)
+            a = torch.empty(M, F, dtype=BF16, device=dev)
+            check(lib.gaot_swiglu_forward(_p(gu), M, F, _p(a), _stream(dev)), "swiglu_forward")
+            w2b = _cast(w2)
+            out = _linear_fwd_raw(a, None, w2b, None, h2)                       # h2 + ffn(h2)
+        ctx.save_for_backward(x2d, s2d, x_in, rstd1, h1, packed, o, lse, h, rstd2, h2b, gu, a,
+                              wsk, wqkv, wob, w13, w2b, n1, n2, fr)
+        ctx.meta = (shape, None if skip is None else skip.shape, B, S, Hd, H, Hkv, d, F, float(p_drop), int(seed),
+                    skip_b is not None)
+        return out.view(shape)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x2d, s2d, x_in, rstd1, h1, packed, o, lse, h, rstd2, h2b, gu, a, wsk, wqkv, wob, w13, w2b, n1, n2, fr) = ctx.saved_tensors
+        shape, skip_shape, B, S, Hd, H, Hkv, d, F, p_drop, seed, has_skip_bias = ctx.meta
+        lib = _lib_()
+        M = B * S
+        dev = dout.device
+        f32 = torch.float32
+        with torch.cuda.device(dev):
+            dout = dout.to(f32).contiguous().view(M, Hd)
+            # ---- FFN: out = h2 + w2(silu(w1 h2) * w3 h2)
+            da = _linear_bwd_x_raw(dout, w2b, BF16)
+            dw2 = torch.empty(Hd, F, dtype=f32, device=dev)
+            _linear_bwd_w_raw(dout, a, dw2)
+            dgu = torch.empty(M, 2 * F, dtype=BF16, device=dev)
+            check(lib.gaot_swiglu_backward(_p(da), _p(gu), M, F, _p(dgu), _stream(dev)), "swiglu_backward")
+            del da
+            dh2 = _linear_bwd_x_raw(dgu, w13, f32, residual=dout)
+            dw13 = torch.empty(2 * F, Hd, dtype=f32, device=dev)
+            _linear_bwd_w_raw(dgu, h2b, dw13)
+            del dgu
+            dh, dn2 = _rmsnorm_bwd(dh2, h, rstd2, n2, None)
+            del dh2
+            # ---- attention: h = x_in + o_proj(attn(norm(x_in)))
+            do = _linear_bwd_x_raw(dh, wob, BF16)
+            dwo = torch.empty(Hd, H * d, dtype=f32, device=dev)
+            _linear_bwd_w_raw(dh, o, dwo)
+            nq, nkv = H * d, Hkv * d
+            dqkv = torch.empty(M, nq + 2 * nkv, dtype=BF16, device=dev)
+            wsb = lib.gaot_attn_fused_backward_workspace_bytes(B, S, H, d)
+            ws = _ws(wsb, dev)
+            with ops._timed("attn_bwd", dev):
+                check(lib.gaot_attn_fused_backward(_p(packed), _p(o), _p(do), _p(lse), B, S, H, Hkv, d, _p(fr), p_drop, seed,
+                                                   _p(ws), wsb, _p(dqkv), dqkv.stride(0), _stream(dev)), "attn_fused_backward")
+            del do, ws
+            dh1 = _linear_bwd_x_raw(dqkv, wqkv, f32)
+            dwqkv = torch.empty(nq + 2 * nkv, Hd, dtype=f32, device=dev)
+            _linear_bwd_w_raw(dqkv, h1, dwqkv)
+            del dqkv
+            dx_in, dn1 = _rmsnorm_bwd(dh1, x_in, rstd1, n1, dh)
+            del dh1, dh
+            dskip = dwsk = dbsk = None
+            if s2d is not None:
+                dcat = _linear_bwd_x_raw(dx_in, wsk, f32)
+                k1 = x2d.shape[1]
+                dx = dcat[:, :k1].reshape(shape)
+                dskip = dcat[:, k1:].reshape(skip_shape)
+                dwsk = torch.empty(wsk.shape, dtype=f32, device=dev)
+                _linear_bwd_w_raw(dx_in, x2d, dwsk[:, :k1])
+                _linear_bwd_w_raw(dx_in, s2d, dwsk[:, k1:])
+                if has_skip_bias:
+                    dbsk = _colsum(dx_in)
+            else:
+                dx = dx_in.view(shape)
+        return (dx, dskip, None, dwsk, dbsk, dn1, dwqkv[:nq], dwqkv[nq:nq + nkv], dwqkv[nq + nkv:], dwo, dn2,
+                dw13[:F], dw2, dw13[F:])
+
+
+def transformer_block(x, skip, *, num_heads: int, num_kv_heads: int, eps: float, rope_freqs: Optional[torch.Tensor],
+                      dropout_p: float, skip_w, skip_b, attn_norm_w, wq, wk, wv, wo, ffn_norm_w, w1, w2, w3,
+                      seed: Optional[int] = None):
+    """Fused TransformerBlock forward (see module docstring).  x [..., S, hidden] fp32; skip like x or None."""
+    ops._need_cuda(x, skip)
+    if dropout_p > 0.0 and seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    cfg = (int(num_heads), int(num_kv_heads), float(eps), rope_freqs, float(dropout_p), int(seed or 0))
+    return _BlockFn.apply(x, skip, cfg, skip_w, skip_b, attn_norm_w, wq, wk, wv, wo, ffn_norm_w, w1, w2, w3)

@@ -167,6 +167,67 @@ int gaot_attn_backward(const float* q, const float* k, const float* v, const flo
                        float dropout_p, uint64_t dropout_seed,
                        void* ws, size_t ws_bytes, float* dq, float* dk, float* dv, void* stream);
 
+/* ------------------------------------------------------------------ token-level dense layers (nn.Linear)
+ * Replaces the fp32 cuBLAS SGEMMs behind nn.Linear of the latent transformer: q/k/v/o_proj
+ *   (reference src/model/layers/attn.py:104-106,:129), SwiGLU w1/w2/w3 (:163), skip_proj over
+ *   cat[x, skip] (:223), patch_linear (src/model/gaot_3d.py:205).  BF16 operands / FP32
+ *   accumulation on tcgen05 (TMEM accumulators); inputs keep their row-major layout, no transposed copies.
+ *   dtype codes: 0 = float32, 1 = bfloat16.  w is the nn.Linear weight [N, K] (row-major, ld = K).
+ *   forward        : y[M,N]  = [x | x2][M,K] w^T (+ bias[N]) (+ residual[M,N]);  x2 (optional) supplies the
+ *                    contraction columns k >= k_split, so cat[x, skip] is never materialised (k_split % 64 == 0)
+ *   backward_input : dx[M,K] = dy[M,N] w (+ residual) (+= when accumulate)
+ *   backward_weight: dw[N,K] = dy^T x (+= when accumulate), split-K with a fixed-order reduction (deterministic)
+ *   Leading dimensions in elements; rows must be 16-byte aligned.  GAOT_ERR_UNSUPPORTED otherwise.
+ */
+size_t gaot_linear_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int gaot_linear_forward(const void* x, int x_dtype, int64_t ldx, const void* x2, int64_t ldx2, int64_t k_split,
+                        const void* w, int w_dtype, int64_t M, int64_t N, int64_t K,
+                        const float* bias, const float* residual, int64_t ldr,
+                        void* y, int y_dtype, int64_t ldy, void* ws, size_t ws_bytes, void* stream);
+int gaot_linear_backward_input(const void* dy, int dy_dtype, int64_t lddy, const void* w, int w_dtype,
+                               int64_t M, int64_t N, int64_t K, const float* residual, int64_t ldr,
+                               void* dx, int dx_dtype, int64_t lddx, int accumulate,
+                               void* ws, size_t ws_bytes, void* stream);
+int gaot_linear_backward_weight(const void* dy, int dy_dtype, int64_t lddy, const void* x, int x_dtype, int64_t ldx,
+                                int64_t M, int64_t N, int64_t K, float* dw, int64_t lddw, int accumulate,
+                                void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------ TransformerBlock row-wise kernels
+ * The pieces of reference src/model/layers/attn.py TransformerBlock.forward (:205-230) between the GEMMs, with
+ * BF16 activations handed from kernel to kernel in the layout the tcgen05 dense kernel reads:
+ *   RMSNorm (:167-178): y = x * rsqrt(mean(x^2) + eps) * w, statistics in fp32; y written as bf16 and/or fp32,
+ *     rstd [M] kept for the backward.  backward: dx (+ dres, the residual-branch gradient) and dw (two-stage,
+ *     fixed-order reduction).  H multiple of 128, <= 1024.
+ *   SwiGLU gate (:163) on the fused [w1 x | w3 x] projection GU [M, 2F] bf16: a = silu(g) * u, and its backward.
+ *   colsum: bias gradient of skip_proj (:223).   cast_bf16: fp32 weights -> bf16 tensor-core operands.
+ */
+int gaot_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+int gaot_rmsnorm_forward(const float* x, const float* w, int64_t M, int32_t H, float eps,
+                         void* y_bf16 /* may be NULL */, float* y_f32 /* may be NULL */, float* rstd /* [M] */, void* stream);
+size_t gaot_rmsnorm_backward_workspace_bytes(int32_t H);
+int gaot_rmsnorm_backward(const float* dy, const float* x, const float* rstd, const float* w,
+                          const float* dres /* may be NULL */, int64_t M, int32_t H,
+                          float* dx, float* dw /* [H] */, void* ws, size_t ws_bytes, void* stream);
+size_t gaot_colsum_workspace_bytes(int64_t M, int64_t N);
+int gaot_colsum(const float* x, int64_t M, int64_t N, float* out /* [N] */, void* ws, size_t ws_bytes, void* stream);
+int gaot_swiglu_forward(const void* gu_bf16, int64_t M, int32_t F, void* a_bf16, void* stream);
+int gaot_swiglu_backward(const void* da_bf16, const void* gu_bf16, int64_t M, int32_t F, void* dgu_bf16, void* stream);
+
+/* latent attention, fused-block flavour (same kernels as gaot_attn_forward/backward): the input is the bf16
+ * output qkv [B*S, ld] of ONE [Wq;Wk;Wv] projection (columns H*d | Hkv*d | Hkv*d); `packed`
+ * (gaot_attn_packed_bytes) receives the per-head bf16 operands with RoPE applied and is handed unchanged to the
+ * backward (no re-packing); out / d_out are bf16 token-major [B*S, H*d]; d_qkv is the bf16 gradient of the
+ * projection output (GQA group summed, RoPE undone), laid out like qkv. */
+size_t gaot_attn_packed_bytes(int64_t B, int64_t S, int32_t H, int32_t Hkv, int32_t d);
+int gaot_attn_fused_forward(const void* qkv_bf16, int64_t ld, int64_t B, int64_t S, int32_t H, int32_t Hkv, int32_t d,
+                            const float* rope_freqs, float dropout_p, uint64_t dropout_seed,
+                            void* packed, void* out_bf16, float* lse, void* stream);
+size_t gaot_attn_fused_backward_workspace_bytes(int64_t B, int64_t S, int32_t H, int32_t d);
+int gaot_attn_fused_backward(const void* packed, const void* out_bf16, const void* d_out_bf16, const float* lse,
+                             int64_t B, int64_t S, int32_t H, int32_t Hkv, int32_t d, const float* rope_freqs,
+                             float dropout_p, uint64_t dropout_seed, void* ws, size_t ws_bytes,
+                             void* d_qkv_bf16, int64_t ld, void* stream);
+
 /* ------------------------------------------------------------------ host-buffer convenience (e2e arm)
  * Same graph build with HOST inputs/outputs: copies positions H2D, runs the kernels,
  * copies the edge list D2H.  Returns E through *E_host; out rows sized by the caller

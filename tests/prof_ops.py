@@ -67,6 +67,27 @@ elif what == "gno":
                 print(f"{name} {prec}: E={E} fwd {fw:.3f} ms ({E / fw / 1e6:.1f} G edges/s... {E / fw * 1e3 / 1e9:.2f} Gedge/s) fwd+bwd {fb:.3f} ms ({E / fb * 1e3 / 1e9:.2f} Gedge/s)")
             except NotImplementedError as e:
                 print(name, prec, "unsupported:", e)
+elif what == "dense":
+    import ctypes
+    lib = _lib.load()
+    M = 16384
+    for N, K in ((256, 256), (768, 256), (1024, 256), (256, 1024), (256, 512)):
+        x = torch.randn(M, K, device=dev, requires_grad=True)
+        w = (torch.randn(N, K, device=dev) / K ** 0.5).requires_grad_(True)
+        go = torch.randn(M, N, device=dev)
+        lib.gaot_profile_enable(1)
+        tf = timeit(lambda: ops.linear(x, w), reps)
+        tfb = timeit(lambda: ops.linear(x, w).backward(go), reps)
+        buf = ctypes.create_string_buffer(4096)
+        lib.gaot_profile_summary(buf, 4096)
+        lib.gaot_profile_enable(0)
+        tt = timeit(lambda: torch.nn.functional.linear(x, w), reps)
+        ttb = timeit(lambda: torch.nn.functional.linear(x, w).backward(go), reps)
+        parts = {l.split()[0]: float(l.split()[2]) / int(l.split()[1]) for l in buf.value.decode().splitlines()}
+        io = lambda *n: sum(n) * 4 / 1e6
+        print(f"M={M} N={N} K={K}: ours fwd {tf*1e3:.1f} us fwd+bwd {tfb*1e3:.1f} us | torch fp32 fwd {tt*1e3:.1f} us fwd+bwd {ttb*1e3:.1f} us | "
+              f"kernels us: " + " ".join(f"{k}={v*1e3:.1f}" for k, v in parts.items()) +
+              f" | fwd HBM floor {io(M*K, N*K, M*N)/6.5e3*1e3:.1f} us")
 elif what == "graph":
     from gaot_3d_b200.graph import get_neighbor_strategy
     for N in (100000, 500000, 1000000, 3160000, 10000000):

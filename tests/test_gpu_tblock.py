@@ -1,0 +1,113 @@
+"""GPU parity of the fused TransformerBlock (gaot_3d_b200/tblock.py, csrc/tblock.cu + dense.cu + attn.cu) against
+the oracle's restatement of reference attn.py:205-230 (oracle/model.py::_block, pinned against the reference's own
+module in tests/test_oracle_vs_reference.py).  BF16 operands / hand-offs -> rtol 2e-2 of the tensor scale (north star)."""
+import pytest
+import torch
+
+from oracle import model as omodel
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp(min=1e-30)).item(), ((a - b).abs().max() / b.abs().max().clamp(min=1e-30)).item()
+
+
+def make_block(hidden, heads, kv, ffn, skip):
+    from gaot_3d_b200.layers.attn import TransformerBlock, AttentionConfig, FFNConfig
+    ac = AttentionConfig(hidden_size=hidden, num_heads=heads, num_kv_heads=kv, atten_dropout=0.0, positional_embedding="rope")
+    fc = FFNConfig(hidden_size=ffn)
+    torch.manual_seed(hidden + heads + ffn)
+    blk = TransformerBlock(hidden, hidden, attn_config=ac, ffn_config=fc, skip_connection=skip)
+    with torch.no_grad():          # non-trivial norm weights
+        blk.attn_norm.weight.uniform_(0.5, 1.5)
+        blk.ffn_norm.weight.uniform_(0.5, 1.5)
+    return blk
+
+
+@pytest.mark.parametrize("B,S,hidden,heads,kv,ffn,skip,rope", [
+    (1, 512, 256, 8, 8, 1024, False, True), (1, 300, 256, 8, 8, 1024, True, True), (2, 200, 128, 4, 2, 256, True, True),
+    (1, 257, 128, 2, 2, 128, False, False)])
+def test_fused_block_vs_oracle(B, S, hidden, heads, kv, ffn, skip, rope):
+    import gaot_3d_b200.layers.attn as A
+    blk = make_block(hidden, heads, kv, ffn, skip)
+    x = torch.randn(B, S, hidden)
+    sk = torch.randn(B, S, hidden) if skip else None
+    go = torch.randn(B, S, hidden)
+    # oracle (CPU fp32 restatement of the reference block)
+    sd = {"b." + k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and "freqs" not in k) for k, v in blk.state_dict().items()}
+    cfg = dict(num_heads=heads, num_kv_heads=kv, norm_eps=1e-6)
+    xr = x.clone().requires_grad_(True)
+    skr = sk.clone().requires_grad_(True) if skip else None
+    ref = omodel._block(sd, "b", xr, cfg, rope, skip=skr)
+    ref.backward(go)
+    # fused path on the GPU
+    blk = blk.to(DEV).train()
+    assert A.FUSED_BLOCK and blk._fused_ok(x.to(DEV), None)
+    xd = x.to(DEV).requires_grad_(True)
+    skd = sk.to(DEV).requires_grad_(True) if skip else None
+    pos = torch.zeros(1) if rope else None
+    out = blk(xd, relative_positions=pos, skip=skd)
+    out.backward(go.to(DEV))
+    checks = [("out", out, ref), ("dx", xd.grad, xr.grad)]
+    if skip:
+        checks.append(("dskip", skd.grad, skr.grad))
+    for n, p in blk.named_parameters():
+        if p.requires_grad:
+            checks.append((n, p.grad, sd["b." + n].grad))
+    for name, a, b in checks:
+        l2, mx = rel(a, b)
+        qk = ".q_proj." in name or ".k_proj." in name     # cancellation-dominated (see test_gpu_model.py)
+        assert l2 < (6e-2 if qk else 2e-2) and mx < (1e-1 if qk else 4e-2), f"{name}: rel l2 {l2:.3e}, rel max {mx:.3e}"
+
+
+def test_fused_equals_modular_path():
+    """The two host paths of the drop-in block run the same math; they differ only by bf16 hand-offs."""
+    import gaot_3d_b200.layers.attn as A
+    blk = make_block(256, 8, 8, 1024, True).to(DEV)
+    x, sk = torch.randn(1, 400, 256, device=DEV), torch.randn(1, 400, 256, device=DEV)
+    pos = torch.zeros(1)
+    outs = []
+    try:
+        for fused in (True, False):
+            A.FUSED_BLOCK = fused
+            outs.append(blk(x, relative_positions=pos, skip=sk))
+    finally:
+        A.FUSED_BLOCK = True
+    l2, mx = rel(outs[0], outs[1])
+    assert l2 < 1e-2 and mx < 2e-2, (l2, mx)
+
+
+def test_rmsnorm_swiglu_colsum_kernels():
+    from gaot_3d_b200 import tblock as T, ops
+    torch.manual_seed(0)
+    M, H, F = 1000, 256, 512
+    x = torch.randn(M, H, device=DEV)
+    w = torch.rand(H, device=DEV) + 0.5
+    yb, yf, rstd = T._rmsnorm_fwd(x, w, 1e-6, True)
+    ref = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6) * w
+    assert torch.allclose(yf, ref, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(yb.float(), ref, rtol=1e-2, atol=1e-2)
+    dy, dres = torch.randn(M, H, device=DEV), torch.randn(M, H, device=DEV)
+    xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    (xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + 1e-6) * wr).backward(dy.double())
+    dx, dw = T._rmsnorm_bwd(dy, x, rstd, w, dres)
+    assert torch.allclose(dx.double(), xr.grad + dres.double(), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(dw.double(), wr.grad, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(T._colsum(dy).double(), dy.double().sum(0), rtol=1e-5, atol=1e-4)
+    # SwiGLU gate on bf16 [g | u]
+    lib = ops._lib_()
+    gu = torch.randn(M, 2 * F, device=DEV).to(torch.bfloat16)
+    a = torch.empty(M, F, dtype=torch.bfloat16, device=DEV)
+    ops.check(lib.gaot_swiglu_forward(ops._p(gu), M, F, ops._p(a), ops._stream(gu.device)), "swiglu")
+    g, u = gu[:, :F].double().requires_grad_(True), gu[:, F:].double().requires_grad_(True)
+    refa = torch.nn.functional.silu(g) * u
+    assert torch.allclose(a.double(), refa, rtol=1e-2, atol=1e-2)
+    da = torch.randn(M, F, device=DEV).to(torch.bfloat16)
+    refa.backward(da.double())
+    dgu = torch.empty(M, 2 * F, dtype=torch.bfloat16, device=DEV)
+    ops.check(lib.gaot_swiglu_backward(ops._p(da), ops._p(gu), M, F, ops._p(dgu), ops._stream(gu.device)), "swiglu_bwd")
+    assert torch.allclose(dgu[:, :F].double(), g.grad, rtol=2e-2, atol=2e-2)
+    assert torch.allclose(dgu[:, F:].double(), u.grad, rtol=2e-2, atol=2e-2)
