@@ -66,7 +66,7 @@ _SIGS = {
     "gaot_swiglu_forward": (c_int, [P, c_int64, c_int32, P, P]),
     "gaot_swiglu_backward": (c_int, [P, P, c_int64, c_int32, P, P]),
     "gaot_attn_packed_bytes": (c_size_t, [c_int64, c_int64, c_int32, c_int32, c_int32]),
-    "gaot_attn_fused_forward": (c_int, [P, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, P, c_float, c_uint64, P, P, P, P]),
+    "gaot_attn_fused_forward": (c_int, [P, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, P, c_float, c_uint64, P, P, P, P, P]),
     "gaot_attn_fused_backward_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32, c_int32]),
     "gaot_attn_fused_backward": (c_int, [P, P, P, P, c_int64, c_int64, c_int32, c_int32, c_int32, P, c_float, c_uint64,
                                          P, c_size_t, P, c_int64, P]),

@@ -96,24 +96,27 @@ attn_pack_qkv_kernel(const bf16* __restrict__ qkv, int64_t ld, bf16* __restrict_
     *reinterpret_cast<uint4*>(dst + ((b * nhd + h) * S + s) * d + ch * 8) = o;
 }
 
-// bf16 variant of the backward prep (fused block: O and dO arrive token-major in bf16)
+// fused-block variant of the backward prep: dO arrives token-major in bf16 (the epilogue of the o_proj dX GEMM), O as
+// the forward's UNROUNDED fp32 copy.  D must cancel against the kernel's own dP = dO_bf16 . V (dS = P (dP - D)), so it
+// is formed from the bf16 dO the MMA consumes and the fp32 O; a bf16-rounded O leaves a 2^-9 error along mean(K) that
+// swamps dQ / dK wherever the attention is close to uniform.
 __global__ void __launch_bounds__(256)
-attn_bwd_prep_bf16_kernel(const bf16* __restrict__ dO, const bf16* __restrict__ O, bf16* __restrict__ dOb,
+attn_bwd_prep_bf16_kernel(const bf16* __restrict__ dO, const float* __restrict__ O, bf16* __restrict__ dOb,
                           float* __restrict__ Dvec, int64_t B, int64_t S, int H, int d) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // (b, s, h)
     if (idx >= B * S * H) return;
     const int h = (int)(idx % H);
     const int64_t s = (idx / H) % S, b = idx / ((int64_t)H * S);
     const bf16* pd = dO + idx * d;
-    const bf16* po = O + idx * d;
+    const float* po = O + idx * d;
     bf16* out = dOb + ((b * H + h) * S + s) * d;
     float acc = 0.f;
     for (int c = 0; c < d; c += 8) {
-        const uint4 a = __ldg(reinterpret_cast<const uint4*>(pd + c)), o = __ldg(reinterpret_cast<const uint4*>(po + c));
-        float fa[8], fo[8];
-        unpack_bf16x8(a, fa); unpack_bf16x8(o, fo);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc = fmaf(fa[i], fo[i], acc);
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(pd + c));
+        const float4 o0 = __ldg(reinterpret_cast<const float4*>(po + c)), o1 = __ldg(reinterpret_cast<const float4*>(po + c + 4));
+        float fa[8];
+        unpack_bf16x8(a, fa);
+        acc += fa[0] * o0.x + fa[1] * o0.y + fa[2] * o0.z + fa[3] * o0.w + fa[4] * o1.x + fa[5] * o1.y + fa[6] * o1.z + fa[7] * o1.w;
         *reinterpret_cast<uint4*>(out + c) = a;
     }
     Dvec[(b * H + h) * S + s] = acc;
@@ -247,7 +250,8 @@ __device__ __forceinline__ bool drop_keep(const DropCfg& dc, uint32_t rowkey, ui
 template <int D, bool DROP>
 __global__ void __launch_bounds__(128, 2)
 attn_fwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const bf16* __restrict__ Vb,
-                void* __restrict__ out_v, int out_bf16, float* __restrict__ lse, int S, int H, int Hkv, float scale_log2, const DropCfg dc) {
+                void* __restrict__ out_v, int out_bf16, float* __restrict__ out32, float* __restrict__ lse, int S, int H, int Hkv,
+                float scale_log2, const DropCfg dc) {
     extern __shared__ __align__(1024) uint8_t sm[];
     __shared__ uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
@@ -430,6 +434,12 @@ attn_fwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
                 pk.x = tc::pack_bf16(O[c] * inv, O[c + 1] * inv); pk.y = tc::pack_bf16(O[c + 2] * inv, O[c + 3] * inv);
                 pk.z = tc::pack_bf16(O[c + 4] * inv, O[c + 5] * inv); pk.w = tc::pack_bf16(O[c + 6] * inv, O[c + 7] * inv);
                 *reinterpret_cast<uint4*>(o + c) = pk;
+            }
+            if (out32) {            // unrounded copy for the backward's D = rowsum(dO * O) (see attn_bwd_prep_bf16_kernel)
+                float* o32 = out32 + ooff;
+#pragma unroll
+                for (int c = 0; c < D; c += 4)
+                    *reinterpret_cast<float4*>(o32 + c) = make_float4(O[c] * inv, O[c + 1] * inv, O[c + 2] * inv, O[c + 3] * inv);
             }
         } else {
             float* o = reinterpret_cast<float*>(out_v) + ooff;
@@ -753,7 +763,7 @@ static DropCfg make_drop(float p, uint64_t seed) {
 }
 
 static int attn_launch_fwd(const AttnWs& w, int64_t B, int64_t S, int H, int Hkv, int d, float dropout_p, uint64_t seed,
-                           void* out, int out_bf16, float* lse, cudaStream_t st) {
+                           void* out, int out_bf16, float* out32, float* lse, cudaStream_t st) {
     GAOT_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "attn: dropout_p must be in [0,1)");
     GAOT_CHECK_ARG((int64_t)B * H * S < ((int64_t)1 << 32), "attn: B*H*S too large for the dropout counter");
     const float scale_log2 = (1.0f / sqrtf((float)d)) * 1.4426950408889634f;
@@ -763,7 +773,7 @@ static int attn_launch_fwd(const AttnWs& w, int64_t B, int64_t S, int H, int Hkv
     GAOT_TIME_KERNEL("attn_fwd", st, 4.0 * (double)B * H * (double)S * (double)S * d);
 #define GAOT_FWD_LAUNCH(DD, DR, SM)                                                                                   \
     do { GAOT_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DD, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM))); \
-         attn_fwd_kernel<DD, DR><<<grid, 128, (SM), st>>>(w.Qb, w.Kb, w.Vb, out, out_bf16, lse, (int)S, H, Hkv, scale_log2, dc); } while (0)
+         attn_fwd_kernel<DD, DR><<<grid, 128, (SM), st>>>(w.Qb, w.Kb, w.Vb, out, out_bf16, out32, lse, (int)S, H, Hkv, scale_log2, dc); } while (0)
     if (d == 32) {
         const size_t smem = 3 * 128 * 32 * 2 + 2 * 128 * 48 * 2 + 128 * 128 * 2;
         if (drop) GAOT_FWD_LAUNCH(32, true, smem); else GAOT_FWD_LAUNCH(32, false, smem);
@@ -786,7 +796,7 @@ int gaot_attn_forward(const float* q, const float* k, const float* v, int64_t B,
     if (!attn_carve(w, ws, ws_bytes, B, S, H, Hkv, d)) { set_error("attn_forward: workspace too small"); return GAOT_ERR_WORKSPACE; }
     rc = attn_prep_all(q, k, v, w, B, S, H, Hkv, d, rope_freqs, st);
     if (rc) return rc;
-    return attn_launch_fwd(w, B, S, H, Hkv, d, dropout_p, seed, out, 0, lse, st);
+    return attn_launch_fwd(w, B, S, H, Hkv, d, dropout_p, seed, out, 0, nullptr, lse, st);
 }
 
 // core backward on prepared operands: w.Qb/Kb/Vb/dOb/Dvec filled -> w.dQacc / dKh / dVh (fp32, per head)
@@ -854,16 +864,16 @@ static void attn_packed_ptrs(AttnWs& w, void* packed, int64_t B, int64_t S, int 
 
 int gaot_attn_fused_forward(const void* qkv, int64_t ld, int64_t B, int64_t S, int32_t H, int32_t Hkv, int32_t d,
                             const float* rope_freqs, float dropout_p, uint64_t seed,
-                            void* packed, void* out, float* lse, void* stream) {
+                            void* packed, void* out, float* out_f32, float* lse, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     int rc = attn_check(B, S, H, Hkv, d);
     if (rc) return rc;
-    GAOT_CHECK_ARG(qkv && packed && out && lse && ld % 8 == 0, "attn_fused_forward: bad pointer / ld");
+    GAOT_CHECK_ARG(qkv && packed && out && out_f32 && lse && ld % 8 == 0, "attn_fused_forward: bad pointer / ld");
     AttnWs w{};
     attn_packed_ptrs(w, packed, B, S, H, Hkv, d);
     attn_pack_qkv_kernel<<<nb256(B * S * (H + 2 * Hkv) * (d / 8)), 256, 0, st>>>((const bf16*)qkv, ld, w.Qb, w.Kb, w.Vb, B, S, H, Hkv, d, rope_freqs);
     GAOT_LAUNCH_CHECK();
-    return attn_launch_fwd(w, B, S, H, Hkv, d, dropout_p, seed, out, 1, lse, st);
+    return attn_launch_fwd(w, B, S, H, Hkv, d, dropout_p, seed, out, 1, out_f32, lse, st);
 }
 
 size_t gaot_attn_fused_backward_workspace_bytes(int64_t B, int64_t S, int32_t H, int32_t d) {
@@ -871,7 +881,7 @@ size_t gaot_attn_fused_backward_workspace_bytes(int64_t B, int64_t S, int32_t H,
     return align_up(qe * 2) + align_up((size_t)B * H * S * 4) + 3 * align_up(qe * 4) + 1024;
 }
 
-int gaot_attn_fused_backward(const void* packed, const void* out, const void* d_out, const float* lse,
+int gaot_attn_fused_backward(const void* packed, const float* out, const void* d_out, const float* lse,
                              int64_t B, int64_t S, int32_t H, int32_t Hkv, int32_t d, const float* rope_freqs,
                              float dropout_p, uint64_t seed, void* ws, size_t ws_bytes,
                              void* d_qkv, int64_t ld, void* stream) {
@@ -886,7 +896,7 @@ int gaot_attn_fused_backward(const void* packed, const void* out, const void* d_
     w.dOb = ar.take<bf16>(qe); w.Dvec = ar.take<float>((size_t)B * H * S);
     w.dQacc = ar.take<float>(qe); w.dKh = ar.take<float>(qe); w.dVh = ar.take<float>(qe);
     if (!ar.ok()) { set_error("attn_fused_backward: workspace too small"); return GAOT_ERR_WORKSPACE; }
-    attn_bwd_prep_bf16_kernel<<<nb256(B * S * H), 256, 0, st>>>((const bf16*)d_out, (const bf16*)out, w.dOb, w.Dvec, B, S, H, d);
+    attn_bwd_prep_bf16_kernel<<<nb256(B * S * H), 256, 0, st>>>((const bf16*)d_out, out, w.dOb, w.Dvec, B, S, H, d);
     GAOT_LAUNCH_CHECK();
     rc = attn_launch_bwd(w, lse, B, S, H, Hkv, d, dropout_p, seed, st);
     if (rc) return rc;

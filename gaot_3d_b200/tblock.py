@@ -111,11 +111,12 @@ class _BlockFn(torch.autograd.Function):
             qkv = _linear_fwd_raw(h1, None, wqkv, None, None, BF16)
             packed = torch.empty(lib.gaot_attn_packed_bytes(B, S, H, Hkv, d), dtype=torch.uint8, device=dev)
             o = torch.empty(M, nq, dtype=BF16, device=dev)
+            o32 = torch.empty(M, nq, dtype=torch.float32, device=dev)        # unrounded copy: the backward's D = rowsum(dO * O)
             lse = torch.empty(B, H, S, dtype=torch.float32, device=dev)
             fr = None if freqs is None else f32(freqs)
             with ops._timed("attn_fwd", dev):
                 check(lib.gaot_attn_fused_forward(_p(qkv), qkv.stride(0), B, S, H, Hkv, d, _p(fr), float(p_drop), int(seed),
-                                                  _p(packed), _p(o), _p(lse), _stream(dev)), "attn_fused_forward")
+                                                  _p(packed), _p(o), _p(o32), _p(lse), _stream(dev)), "attn_fused_forward")
             del qkv
             wob = _cast(wo)
             h = _linear_fwd_raw(o, None, wob, None, x_in)                       # x + attn(norm(x))
@@ -128,7 +129,7 @@ class _BlockFn(torch.autograd.Function):
             check(lib.gaot_swiglu_forward(_p(gu), M, F, _p(a), _stream(dev)), "swiglu_forward")
             w2b = _cast(w2)
             out = _linear_fwd_raw(a, None, w2b, None, h2)                       # h2 + ffn(h2)
-        ctx.save_for_backward(x2d, s2d, x_in, rstd1, h1, packed, o, lse, h, rstd2, h2b, gu, a,
+        ctx.save_for_backward(x2d, s2d, x_in, rstd1, h1, packed, o, o32, lse, h, rstd2, h2b, gu, a,
                               wsk, wqkv, wob, w13, w2b, n1, n2, fr)
         ctx.meta = (shape, None if skip is None else skip.shape, B, S, Hd, H, Hkv, d, F, float(p_drop), int(seed),
                     skip_b is not None)
@@ -136,7 +137,7 @@ class _BlockFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
-        (x2d, s2d, x_in, rstd1, h1, packed, o, lse, h, rstd2, h2b, gu, a, wsk, wqkv, wob, w13, w2b, n1, n2, fr) = ctx.saved_tensors
+        (x2d, s2d, x_in, rstd1, h1, packed, o, o32, lse, h, rstd2, h2b, gu, a, wsk, wqkv, wob, w13, w2b, n1, n2, fr) = ctx.saved_tensors
         shape, skip_shape, B, S, Hd, H, Hkv, d, F, p_drop, seed, has_skip_bias = ctx.meta
         lib = _lib_()
         M = B * S
@@ -166,7 +167,7 @@ class _BlockFn(torch.autograd.Function):
             wsb = lib.gaot_attn_fused_backward_workspace_bytes(B, S, H, d)
             ws = _ws(wsb, dev)
             with ops._timed("attn_bwd", dev):
-                check(lib.gaot_attn_fused_backward(_p(packed), _p(o), _p(do), _p(lse), B, S, H, Hkv, d, _p(fr), p_drop, seed,
+                check(lib.gaot_attn_fused_backward(_p(packed), _p(o32), _p(do), _p(lse), B, S, H, Hkv, d, _p(fr), p_drop, seed,
                                                    _p(ws), wsb, _p(dqkv), dqkv.stride(0), _stream(dev)), "attn_fused_backward")
             del do, ws
             dh1 = _linear_bwd_x_raw(dqkv, wqkv, f32)

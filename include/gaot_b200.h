@@ -216,14 +216,15 @@ int gaot_swiglu_backward(const void* da_bf16, const void* gu_bf16, int64_t M, in
 /* latent attention, fused-block flavour (same kernels as gaot_attn_forward/backward): the input is the bf16
  * output qkv [B*S, ld] of ONE [Wq;Wk;Wv] projection (columns H*d | Hkv*d | Hkv*d); `packed`
  * (gaot_attn_packed_bytes) receives the per-head bf16 operands with RoPE applied and is handed unchanged to the
- * backward (no re-packing); out / d_out are bf16 token-major [B*S, H*d]; d_qkv is the bf16 gradient of the
+ * backward (no re-packing); out_bf16 / d_out are bf16 token-major [B*S, H*d], out_f32 is the same output unrounded
+ * (the backward forms D = rowsum(dO * O) from it; a rounded O costs q/k-gradient accuracy); d_qkv is the bf16 gradient of the
  * projection output (GQA group summed, RoPE undone), laid out like qkv. */
 size_t gaot_attn_packed_bytes(int64_t B, int64_t S, int32_t H, int32_t Hkv, int32_t d);
 int gaot_attn_fused_forward(const void* qkv_bf16, int64_t ld, int64_t B, int64_t S, int32_t H, int32_t Hkv, int32_t d,
                             const float* rope_freqs, float dropout_p, uint64_t dropout_seed,
-                            void* packed, void* out_bf16, float* lse, void* stream);
+                            void* packed, void* out_bf16, float* out_f32, float* lse, void* stream);
 size_t gaot_attn_fused_backward_workspace_bytes(int64_t B, int64_t S, int32_t H, int32_t d);
-int gaot_attn_fused_backward(const void* packed, const void* out_bf16, const void* d_out_bf16, const float* lse,
+int gaot_attn_fused_backward(const void* packed, const float* out_f32, const void* d_out_bf16, const float* lse,
                              int64_t B, int64_t S, int32_t H, int32_t Hkv, int32_t d, const float* rope_freqs,
                              float dropout_p, uint64_t dropout_seed, void* ws, size_t ws_bytes,
                              void* d_qkv_bf16, int64_t ld, void* stream);
