@@ -24,6 +24,16 @@ namespace gaot {
 
 using bf16 = __nv_bfloat16;
 
+// --------------------------------------------------------------------------- operand layouts
+// K and V stay row-major bf16 [B,Hkv,S,d].  Q and dO are stored PRE-TILED: per (b,h) ceil(S/128) tiles of 128 rows, each
+// tile already in the kernels' chunk-major shared-memory layout (tc05.cuh: 16-byte chunk c of row r at c*128*16 + r*16),
+// rows >= S zero.  A tile is therefore one contiguous 128*d*2-byte block that the backward's loader moves with a single
+// cp.async.bulk (TMA engine, async proxy: no generic->async proxy fence in front of the tensor core).
+__host__ __device__ __forceinline__ int64_t pad128(int64_t S) { return (S + 127) / 128 * 128; }
+__device__ __forceinline__ size_t tiled_off(int64_t head, int64_t S_pad, int64_t s, int d, int ch) {
+    return ((size_t)head * S_pad + (size_t)(s & ~(int64_t)127)) * d + (size_t)ch * (128 * 8) + (size_t)(s & 127) * 8;
+}
+
 // --------------------------------------------------------------------------- prep kernels
 // fp32 [B,S,nh*d] (token-major projection output) -> bf16 [B,nh,S,d], optional RoPE.
 template <bool ROPE>
@@ -43,23 +53,27 @@ __device__ __forceinline__ void rope8(float (&x)[8], int s, int c0, const float*
 
 __global__ void __launch_bounds__(256)
 attn_prep_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t B, int64_t S, int nh, int d,
-                 const float* __restrict__ freqs /* NULL: no rope */) {
+                 const float* __restrict__ freqs /* NULL: no rope */, int tiled) {
     const int cpr = d >> 3;                                   // 8-element chunks per head row
-    const int64_t total = B * S * nh * cpr;
+    const int64_t Sx = tiled ? pad128(S) : S;
+    const int64_t total = B * Sx * nh * cpr;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int ch = (int)(idx % cpr);
     const int h = (int)((idx / cpr) % nh);
-    const int64_t s = (idx / ((int64_t)cpr * nh)) % S;
-    const int64_t b = idx / ((int64_t)cpr * nh * S);
-    const float* p = src + ((b * S + s) * nh + h) * d + ch * 8;
-    const float4 v0 = *reinterpret_cast<const float4*>(p), v1 = *reinterpret_cast<const float4*>(p + 4);
-    float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-    if (freqs) rope8<true>(x, (int)s, ch * 8, freqs, false);
-    uint4 o;
-    o.x = tc::pack_bf16(x[0], x[1]); o.y = tc::pack_bf16(x[2], x[3]);
-    o.z = tc::pack_bf16(x[4], x[5]); o.w = tc::pack_bf16(x[6], x[7]);
-    *reinterpret_cast<uint4*>(dst + ((b * nh + h) * S + s) * d + ch * 8) = o;
+    const int64_t s = (idx / ((int64_t)cpr * nh)) % Sx;
+    const int64_t b = idx / ((int64_t)cpr * nh * Sx);
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (s < S) {
+        const float* p = src + ((b * S + s) * nh + h) * d + ch * 8;
+        const float4 v0 = *reinterpret_cast<const float4*>(p), v1 = *reinterpret_cast<const float4*>(p + 4);
+        float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        if (freqs) rope8<true>(x, (int)s, ch * 8, freqs, false);
+        o.x = tc::pack_bf16(x[0], x[1]); o.y = tc::pack_bf16(x[2], x[3]);
+        o.z = tc::pack_bf16(x[4], x[5]); o.w = tc::pack_bf16(x[6], x[7]);
+    }
+    bf16* out = tiled ? dst + tiled_off(b * nh + h, Sx, s, d, ch) : dst + ((b * nh + h) * S + s) * d + ch * 8;
+    *reinterpret_cast<uint4*>(out) = o;
 }
 
 // fused-projection variant: qkv bf16 [B*S, ld] (columns: H*d of q | Hkv*d of k | Hkv*d of v, the output of
@@ -73,18 +87,23 @@ __global__ void __launch_bounds__(256)
 attn_pack_qkv_kernel(const bf16* __restrict__ qkv, int64_t ld, bf16* __restrict__ Qb, bf16* __restrict__ Kb,
                      bf16* __restrict__ Vb, int64_t B, int64_t S, int H, int Hkv, int d, const float* __restrict__ freqs) {
     const int cpr = d >> 3, nh = H + 2 * Hkv;
-    const int64_t total = B * S * nh * cpr;
+    const int64_t Sp = pad128(S);
+    const int64_t total = B * Sp * nh * cpr;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int ch = (int)(idx % cpr);
     const int hh = (int)((idx / cpr) % nh);
-    const int64_t s = (idx / ((int64_t)cpr * nh)) % S;
-    const int64_t b = idx / ((int64_t)cpr * nh * S);
+    const int64_t s = (idx / ((int64_t)cpr * nh)) % Sp;
+    const int64_t b = idx / ((int64_t)cpr * nh * Sp);
+    if (s >= S) {                                             // padding rows exist only in the pre-tiled Q
+        if (hh < H) *reinterpret_cast<uint4*>(Qb + tiled_off(b * H + hh, Sp, s, d, ch)) = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
     const uint4 raw = __ldg(reinterpret_cast<const uint4*>(qkv + (b * S + s) * ld + (int64_t)hh * d + ch * 8));
-    bf16* dst; int h, nhd; bool rope;
-    if (hh < H) { dst = Qb; h = hh; nhd = H; rope = true; }
-    else if (hh < H + Hkv) { dst = Kb; h = hh - H; nhd = Hkv; rope = true; }
-    else { dst = Vb; h = hh - H - Hkv; nhd = Hkv; rope = false; }
+    bf16* dst; bool rope;
+    if (hh < H) { dst = Qb + tiled_off(b * H + hh, Sp, s, d, ch); rope = true; }
+    else if (hh < H + Hkv) { dst = Kb + ((b * Hkv + (hh - H)) * S + s) * d + ch * 8; rope = true; }
+    else { dst = Vb + ((b * Hkv + (hh - H - Hkv)) * S + s) * d + ch * 8; rope = false; }
     uint4 o = raw;
     if (rope && freqs) {
         float x[8];
@@ -93,7 +112,7 @@ attn_pack_qkv_kernel(const bf16* __restrict__ qkv, int64_t ld, bf16* __restrict_
         o.x = tc::pack_bf16(x[0], x[1]); o.y = tc::pack_bf16(x[2], x[3]);
         o.z = tc::pack_bf16(x[4], x[5]); o.w = tc::pack_bf16(x[6], x[7]);
     }
-    *reinterpret_cast<uint4*>(dst + ((b * nhd + h) * S + s) * d + ch * 8) = o;
+    *reinterpret_cast<uint4*>(dst) = o;
 }
 
 // fused-block variant of the backward prep: dO arrives token-major in bf16 (the epilogue of the o_proj dX GEMM), O as
@@ -103,13 +122,18 @@ attn_pack_qkv_kernel(const bf16* __restrict__ qkv, int64_t ld, bf16* __restrict_
 __global__ void __launch_bounds__(256)
 attn_bwd_prep_bf16_kernel(const bf16* __restrict__ dO, const float* __restrict__ O, bf16* __restrict__ dOb,
                           float* __restrict__ Dvec, int64_t B, int64_t S, int H, int d) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // (b, s, h)
-    if (idx >= B * S * H) return;
+    const int64_t Sp = pad128(S);
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // (b, s, h) over the padded length
+    if (idx >= B * Sp * H) return;
     const int h = (int)(idx % H);
-    const int64_t s = (idx / H) % S, b = idx / ((int64_t)H * S);
-    const bf16* pd = dO + idx * d;
-    const float* po = O + idx * d;
-    bf16* out = dOb + ((b * H + h) * S + s) * d;
+    const int64_t s = (idx / H) % Sp, b = idx / ((int64_t)H * Sp);
+    bf16* out = dOb + tiled_off(b * H + h, Sp, s, d, 0);
+    if (s >= S) {
+        for (int c = 0; c < d; c += 8) *reinterpret_cast<uint4*>(out + (c >> 3) * (128 * 8)) = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
+    const bf16* pd = dO + ((b * S + s) * H + h) * d;
+    const float* po = O + ((b * S + s) * H + h) * d;
     float acc = 0.f;
     for (int c = 0; c < d; c += 8) {
         const uint4 a = __ldg(reinterpret_cast<const uint4*>(pd + c));
@@ -117,7 +141,7 @@ attn_bwd_prep_bf16_kernel(const bf16* __restrict__ dO, const float* __restrict__
         float fa[8];
         unpack_bf16x8(a, fa);
         acc += fa[0] * o0.x + fa[1] * o0.y + fa[2] * o0.z + fa[3] * o0.w + fa[4] * o1.x + fa[5] * o1.y + fa[6] * o1.z + fa[7] * o1.w;
-        *reinterpret_cast<uint4*>(out + c) = a;
+        *reinterpret_cast<uint4*>(out + (c >> 3) * (128 * 8)) = a;
     }
     Dvec[(b * H + h) * S + s] = acc;
 }
@@ -157,13 +181,18 @@ attn_bwd_post_qkv_kernel(const float* __restrict__ dQh, const float* __restrict_
 __global__ void __launch_bounds__(256)
 attn_bwd_prep_kernel(const float* __restrict__ dO, const float* __restrict__ O, bf16* __restrict__ dOb,
                      float* __restrict__ Dvec, int64_t B, int64_t S, int H, int d) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // (b, s, h)
-    if (idx >= B * S * H) return;
+    const int64_t Sp = pad128(S);
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // (b, s, h) over the padded length
+    if (idx >= B * Sp * H) return;
     const int h = (int)(idx % H);
-    const int64_t s = (idx / H) % S, b = idx / ((int64_t)H * S);
-    const float* pd = dO + idx * d;
-    const float* po = O + idx * d;
-    bf16* out = dOb + ((b * H + h) * S + s) * d;
+    const int64_t s = (idx / H) % Sp, b = idx / ((int64_t)H * Sp);
+    bf16* out = dOb + tiled_off(b * H + h, Sp, s, d, 0);
+    if (s >= S) {
+        for (int c = 0; c < d; c += 8) *reinterpret_cast<uint4*>(out + (c >> 3) * (128 * 8)) = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
+    const float* pd = dO + ((b * S + s) * H + h) * d;
+    const float* po = O + ((b * S + s) * H + h) * d;
     float acc = 0.f;
     for (int c = 0; c < d; c += 8) {
         const float4 a0 = *reinterpret_cast<const float4*>(pd + c), a1 = *reinterpret_cast<const float4*>(pd + c + 4);
@@ -172,7 +201,7 @@ attn_bwd_prep_kernel(const float* __restrict__ dO, const float* __restrict__ O, 
         uint4 o;
         o.x = tc::pack_bf16(a0.x, a0.y); o.y = tc::pack_bf16(a0.z, a0.w);
         o.z = tc::pack_bf16(a1.x, a1.y); o.w = tc::pack_bf16(a1.z, a1.w);
-        *reinterpret_cast<uint4*>(out + c) = o;
+        *reinterpret_cast<uint4*>(out + (c >> 3) * (128 * 8)) = o;
     }
     Dvec[(b * H + h) * S + s] = acc;
 }
@@ -209,6 +238,14 @@ __device__ __forceinline__ void load_row(const bf16* __restrict__ g, bool valid,
 #pragma unroll
     for (int c = 0; c < D / 8; ++c)
         r[c] = valid ? *reinterpret_cast<const uint4*>(g + c * 8) : make_uint4(0u, 0u, 0u, 0u);
+}
+// row `s` of a pre-tiled operand (head base `g`, see tiled_off)
+template <int D>
+__device__ __forceinline__ void load_row_tiled(const bf16* __restrict__ g, int64_t s, bool valid, uint4 (&r)[D / 8]) {
+    const bf16* p = g + (size_t)(s & ~(int64_t)127) * D + (size_t)(s & 127) * 8;
+#pragma unroll
+    for (int c = 0; c < D / 8; ++c)
+        r[c] = valid ? *reinterpret_cast<const uint4*>(p + c * (128 * 8)) : make_uint4(0u, 0u, 0u, 0u);
 }
 template <int D>
 __device__ __forceinline__ void store_row(uint8_t* tile, int row, const uint4 (&r)[D / 8]) {
@@ -251,7 +288,7 @@ template <int D, bool DROP>
 __global__ void __launch_bounds__(128, 2)
 attn_fwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const bf16* __restrict__ Vb,
                 void* __restrict__ out_v, int out_bf16, float* __restrict__ out32, float* __restrict__ lse, int S, int H, int Hkv,
-                float scale_log2, const DropCfg dc) {
+                float scale_log2, int debug, const DropCfg dc) {
     extern __shared__ __align__(1024) uint8_t sm[];
     __shared__ uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
@@ -276,7 +313,7 @@ attn_fwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
     uint4 kreg[D / 8], vreg[D / 8];                     // register-staged K/V rows of a future tile
     {
         uint4 r[D / 8];
-        load_row<D>(Qb + ((size_t)(b * H + h) * S + (valid_q ? q : 0)) * D, valid_q, r);
+        load_row_tiled<D>(Qb + (size_t)(b * H + h) * pad128(S) * D, valid_q ? q : 0, valid_q, r);
         store_row<D>(Qs, tid, r);
         const bool vk = tid < S;
         load_row<D>(Kbase + (size_t)(vk ? tid : 0) * D, vk, r);
@@ -377,9 +414,11 @@ attn_fwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
             for (int c = 0; c < 128; ++c) if (c >= kvalid) sv[c] = -INFINITY;
         }
         float mr = fmax3(sv[0], sv[1], sv[2]);
+        if (!(debug & 64)) {
 #pragma unroll
         for (int c = 3; c + 1 < 128; c += 2) mr = fmax3(mr, sv[c], sv[c + 1]);
         mr = fmaxf(mr, sv[127]);
+        }
         const float mx = fmaxf(m, mr * scale_log2);
         alpha_prev = ex2_approx(m - mx);                // m = -inf on the first tile -> 0
         const float nmx = -mx;
@@ -389,7 +428,8 @@ attn_fwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
             float p[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                p[c] = ex2_approx(fmaf(sv[c8 * 8 + c], scale_log2, nmx));
+                p[c] = fmaf(sv[c8 * 8 + c], scale_log2, nmx);
+                if (!(debug & 32)) p[c] = ex2_approx(p[c]);
                 if (DROP) {
                     rs += p[c];
                     p[c] = drop_keep(dc, rowkey, (uint32_t)(j * 128 + c8 * 8 + c)) ? p[c] * dc.inv_keep : 0.f;
@@ -491,7 +531,7 @@ attn_bwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
     const size_t stat_off = ((size_t)b * H + h) * S;
     const int nq = (S + 127) / 128;
     constexpr uint32_t TM_ST = 0, TM_DPT = 64, TM_DV = 128, TM_DK = 128 + D, TM_DQ = 128 + 2 * D;
-    const bf16* tile_src = (half == 0 ? Qb : dOb) + head_off;
+    const bf16* tile_src = (half == 0 ? Qb : dOb) + (size_t)(b * H + h) * pad128(S) * D;   // pre-tiled operands
     const float* stat_src = (half == 0 ? lse : Dvec) + stat_off;
 
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, TM_COLS);
@@ -504,7 +544,7 @@ attn_bwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
         load_row<D>(base, valid_k, r);
         store_row<D>(half == 0 ? Kt : Vt, row, r);
         const bool vq = row < S;                     // query tile 0 -> buffer 0
-        load_row<D>(tile_src + (size_t)(vq ? row : 0) * D, vq, r);
+        load_row_tiled<D>(tile_src, vq ? row : 0, vq, r);
         store_row<D>(half == 0 ? Qs : dOs, row, r);
         const float st0 = vq ? stat_src[row] : (half == 0 ? INFINITY : 0.f);
         if (half == 0) nlse_s[0][row] = -st0; else D_s[0][row] = st0;
@@ -512,7 +552,7 @@ attn_bwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
         if (nq > 1) {                                // tile 1 -> registers
             const int qn = 128 + row;
             const bool v1 = qn < S;
-            load_row<D>(tile_src + (size_t)(v1 ? qn : 0) * D, v1, nreg);
+            load_row_tiled<D>(tile_src, v1 ? qn : 0, v1, nreg);
             nstat = v1 ? stat_src[qn] : (half == 0 ? INFINITY : 0.f);
         }
     }
@@ -597,8 +637,8 @@ attn_bwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
         for (int hq = 0; hq < 2; ++hq) {
             tc::mbar_wait(&mbar, ph); ph ^= 1;        // scores of (i, hq) ready; every earlier MMA has completed
             tc::fence_after_sync();
-            if (hq == 0 && i > 0) dq_epilogue((i - 1) * 128);
-            {
+            if (hq == 0 && i > 0 && !(debug & 8)) dq_epilogue((i - 1) * 128);
+            if (!(debug & 16)) {
                 const int c0 = half * 32;             // this thread's 32 query columns of the half
                 float st[32], dp[32];
                 {
@@ -628,7 +668,8 @@ attn_bwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
                     float p[8], ds[8];
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        p[c] = ex2_approx(fmaf(st[c8 * 8 + c], scale_log2, nl[c]));
+                        p[c] = fmaf(st[c8 * 8 + c], scale_log2, nl[c]);
+                        if (!(debug & 2)) p[c] = ex2_approx(p[c]);
                         if (DROP) {
                             const float mk = (lowbias32(rk_p[c8 * 8 + c] ^ kterm) >= dc.thresh) ? dc.inv_keep : 0.f;
                             ds[c] = p[c] * fmaf(dp[c8 * 8 + c], mk, -dd[c]);
@@ -653,7 +694,7 @@ attn_bwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
                 if (i + 2 < nq) {
                     const int qn = (i + 2) * 128 + row;
                     const bool vq = qn < S;
-                    load_row<D>(tile_src + (size_t)(vq ? qn : 0) * D, vq, nreg);
+                    load_row_tiled<D>(tile_src, vq ? qn : 0, vq, nreg);
                     nstat = vq ? stat_src[qn] : (half == 0 ? INFINITY : 0.f);
                 }
             }
@@ -672,7 +713,7 @@ attn_bwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
                     for (int s = 0; s < 4; ++s)   // dK[key,d] += dS^T[key, 64 q] Q[64 q, d]
                         tc::mma_bf16(tmem + TM_DK, kdS.adv((hq * 4 + s) * KS).u64(), mQ.adv(off + s * tc::KSTEP_MN).u64(), idescKM,
                                      (i > 0) || (hq > 0) || (s > 0));
-                    if (hq == 1) {
+                    if (hq == 1 && !(debug & 4)) {
 #pragma unroll
                         for (int s = 0; s < 8; ++s)   // dQ[q,d] = dS[q, key] K[key, d] over all 128 queries of the tile
                             tc::mma_bf16(tmem + TM_DQ, mdS.adv(s * tc::KSTEP_MN).u64(), mK.adv(s * tc::KSTEP_MN).u64(), idescMM, s > 0);
@@ -707,19 +748,351 @@ attn_bwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
     if (warp == 0) tc::tmem_dealloc(tmem, TM_COLS);
 }
 
+// --------------------------------------------------------------------------- backward, warp-specialised (head_dim 32)
+// One CTA per SM owns 128 keys of one (batch, head) and walks the query tiles in 64-query steps; the step's scores live
+// in one of TWO TMEM stages, so the tensor core computes the scores of step n+2 while the compute warps are busy with
+// step n+1, and the accumulator products of step n (dV, dK, dQ) drain behind them.  Nothing in the loop is a CTA-wide
+// barrier; the roles talk through mbarriers:
+//   compute warps (16): wait scores(n) -> tcgen05.ld S^T, dP^T (16 columns each) -> P^T = exp2(S^T c - lse),
+//                       dS^T = P^T (dP^T - D) -> bf16 chunk-major tiles -> arrive(cmp[n&1])
+//   MMA warp (1 lane) : wait cmp[n&1] -> scores(n+2) into the stage just read -> commit(S[n&1]);
+//                       dV += P^T dO, dK += dS^T Q, (second half) dQ = dS K -> commit(acc[n&1])
+//   drain warps (4)   : wait acc of a tile's second step -> tcgen05.ld dQ (128 queries x 32) -> arrive(dq) -> scaled rows
+//                       to a linear 4 KB staging block -> ONE cp.reduce.async.bulk (.add.f32) per warp into global dQ
+//   loader warp (1)   : Q / dO tiles (cp.async, 16-byte chunks scattered into the chunk-major layout) and lse / D / dropout
+//                       row keys, three tiles deep, released by the accumulator barrier of the tile that used the buffer
+// TMEM (512 columns): stage s: S^T at 128 s, dP^T at 128 s + 64; dV 256; dK 288; dQ (two tiles in flight) 320 + 32 b.
+__device__ long long g_bw2_ts[1024];
+namespace bw2 {
+constexpr int D = 32;
+constexpr int TILE_B = 128 * D * 2;                 // 8 KB: one 128-row x 32 bf16 tile
+constexpr int PT_B = 128 * 64 * 2;                  // 16 KB: P^T of one step
+constexpr int DS_B = 128 * 128 * 2;                 // 32 KB: dS^T of one query tile
+constexpr int NLB = 4;                              // Q / dO tile buffers
+constexpr int OFF_K = 0, OFF_V = TILE_B, OFF_Q = 2 * TILE_B, OFF_DO = (2 + NLB) * TILE_B, OFF_PT = (2 + 2 * NLB) * TILE_B;
+constexpr int OFF_DS = OFF_PT + 2 * PT_B, OFF_STG = OFF_DS + 2 * DS_B;
+constexpr int SMEM = OFF_STG + 4 * 4096;            // 196608 B
+constexpr uint32_t TM_DV = 256, TM_DK = 288, TM_DQ = 320;
+}
+
+template <int NCW, bool DROP>
+__global__ void __launch_bounds__((NCW + 6) * 32, 1)
+attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const bf16* __restrict__ Vb,
+                 const bf16* __restrict__ dOb, const float* __restrict__ lse, const float* __restrict__ Dvec,
+                 float* __restrict__ dQacc, float* __restrict__ dKh, float* __restrict__ dVh,
+                 int S, int H, int Hkv, float scale, float scale_log2, int debug, const DropCfg dc) {
+    using namespace bw2;
+    constexpr int CG = NCW / 4;                      // column groups of a 64-query step
+    constexpr int CPT = 64 / CG;                     // score columns per compute thread (16 or 32)
+    constexpr int CQ = D / CG;                       // dK / dV columns per compute thread in the epilogue
+    constexpr int W_DRAIN = NCW, W_MMA = NCW + 4, W_LOAD = NCW + 5;
+    extern __shared__ __align__(1024) uint8_t sm[];
+    __shared__ uint64_t bar_S[2], bar_acc[2], bar_cmp[2], bar_load[NLB], bar_dq[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float lse_s[NLB][128];    // zero-filled for padding queries (see the loader)
+    __shared__ __align__(16) float D_s[NLB][128];
+    __shared__ __align__(16) uint32_t rk_s[NLB][128];  // DROP: per-query row keys
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * 128;
+    const int kvh = h / (H / Hkv);
+    const size_t head_off = ((size_t)(b * H + h) * S) * D;
+    const size_t stat_off = ((size_t)b * H + h) * S;
+    const int nq = (S + 127) / 128, nsteps = 2 * nq;
+
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+    if (tid == 32) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&bar_S[i], 1); tc::mbar_init(&bar_acc[i], 1); tc::mbar_init(&bar_cmp[i], NCW); tc::mbar_init(&bar_dq[i], 4);
+        }
+#pragma unroll
+        for (int i = 0; i < NLB; ++i) tc::mbar_init(&bar_load[i], DROP ? 34 : 33);
+        tc::mbar_fence_init();
+    }
+    if (tid < 256) {                                  // K / V tiles of this CTA (resident for the whole kernel)
+        const int row = tid & 127, which = tid >> 7;
+        const bool vk = k0 + row < S;
+        uint4 r[D / 8];
+        load_row<D>((which == 0 ? Kb : Vb) + ((size_t)(b * Hkv + kvh) * S + (vk ? k0 + row : 0)) * D, vk, r);
+        store_row<D>(sm + (which == 0 ? OFF_K : OFF_V), row, r);
+    }
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t sbase = tc::smem_u32(sm);
+
+    if (warp == W_LOAD) {
+        // ------------------------------------------------------------------ loader (fire and forget)
+        // Q / dO tiles are pre-tiled in global memory (see "operand layouts"): one 8 KB cp.async.bulk each, completion
+        // counted in bytes on bar_load -- async-proxy writes, so the MMA lane needs no proxy fence.  lse / D ride on
+        // 4-byte cp.async whose completion every lane signals with cp.async.mbarrier.arrive.noinc (32 + 1 arrivals per
+        // tile).  Padding queries are zero-filled: Q = dO = 0, lse = D = 0 give P = 1, dP = 0, dS = 0, and P^T only
+        // multiplies the zero dO rows.  The loader blocks only on a buffer being released: up to NLB - 1 tiles ahead.
+        const bf16* qsrc = Qb + (size_t)(b * H + h) * nq * 128 * D;
+        const bf16* dsrc = dOb + (size_t)(b * H + h) * nq * 128 * D;
+        for (int t = 0; t < nq; ++t) {
+            const int buf = t % NLB;
+            if (t >= NLB) tc::mbar_wait(&bar_acc[1], (uint32_t)((t - NLB) & 1));   // every MMA that read this buffer has completed
+            if (lane == 0 && !((debug & 2) && t >= NLB)) {
+                tc::mbar_arrive_expect_tx(&bar_load[buf], 2 * TILE_B);
+                tc::bulk_copy_g2s(sbase + OFF_Q + buf * TILE_B, qsrc + (size_t)t * 128 * D, TILE_B, &bar_load[buf]);
+                tc::bulk_copy_g2s(sbase + OFF_DO + buf * TILE_B, dsrc + (size_t)t * 128 * D, TILE_B, &bar_load[buf]);
+            } else if (lane == 0) {
+                tc::mbar_arrive(&bar_load[buf]);
+            }
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int r = it * 32 + lane, q = t * 128 + r;
+                const bool ok = q < S;
+                tc::cp_async4(tc::smem_u32(&lse_s[buf][r]), ok ? (const void*)(lse + stat_off + q) : (const void*)lse, ok);
+                tc::cp_async4(tc::smem_u32(&D_s[buf][r]), ok ? (const void*)(Dvec + stat_off + q) : (const void*)Dvec, ok);
+                if (DROP) rk_s[buf][r] = drop_rowkey(dc, (uint32_t)(stat_off + q));
+            }
+            tc::cp_async_mbar_arrive_noinc(&bar_load[buf]);
+            if (DROP) { __syncwarp(); if (lane == 0) tc::mbar_arrive(&bar_load[buf]); }   // releases the row-key stores
+        }
+        tc::cp_async_wait_all();
+    } else if (warp == W_MMA) {
+        // ------------------------------------------------------------------ tensor-core issue (one lane)
+        if (tc::elect_one()) {
+            constexpr uint32_t idesc64 = tc::make_idesc_bf16(128, 64, 0, 0);
+            constexpr uint32_t idescKM = tc::make_idesc_bf16(128, D, 0, 1);     // A K-major, B MN-major
+            constexpr uint32_t idescMM = tc::make_idesc_bf16(128, D, 1, 1);     // A MN-major, B MN-major
+            constexpr uint32_t KS = tc::kstep_kmajor(128);
+            const tc::Desc kK = tc::kmajor(sbase + OFF_K, 128), kV = tc::kmajor(sbase + OFF_V, 128), mK = tc::mnmajor(sbase + OFF_K, 128);
+            const tc::Desc kQ = tc::kmajor(sbase + OFF_Q, 128), kdO = tc::kmajor(sbase + OFF_DO, 128);
+            const tc::Desc mQ = tc::mnmajor(sbase + OFF_Q, 128), mdO = tc::mnmajor(sbase + OFF_DO, 128);
+            const tc::Desc kPT = tc::kmajor(sbase + OFF_PT, 128), kdS = tc::kmajor(sbase + OFF_DS, 128), mdS = tc::mnmajor(sbase + OFF_DS, 128);
+            auto issue_scores = [&](int n) {
+                const uint32_t off = ((n >> 1) % NLB) * TILE_B + (n & 1) * 64 * 16;
+                const uint32_t tS = tmem + (uint32_t)(n & 1) * 128u;
+#pragma unroll
+                for (int s = 0; s < D / 16; ++s)
+                    tc::mma_bf16(tS, kK.adv(s * KS).u64(), kQ.adv(off + s * KS).u64(), idesc64, s > 0);
+#pragma unroll
+                for (int s = 0; s < D / 16; ++s)
+                    tc::mma_bf16(tS + 64, kV.adv(s * KS).u64(), kdO.adv(off + s * KS).u64(), idesc64, s > 0);
+            };
+            tc::mbar_wait(&bar_load[0], 0);
+            issue_scores(0); tc::mma_commit(&bar_S[0]);
+            issue_scores(1); tc::mma_commit(&bar_S[1]);
+            for (int n = 0; n < nsteps; ++n) {
+                const int i = n >> 1, hq = n & 1, s = n & 1;
+                tc::mbar_wait(&bar_cmp[s], (uint32_t)((n >> 1) & 1));           // P^T / dS^T of step n written, stage s drained
+                tc::fence_after_sync();
+                const bool ts = (debug & 512) && blockIdx.x == 0 && blockIdx.y == 0 && n < 32;
+                if (ts) g_bw2_ts[n * 8 + 0] = clock64();
+                if (n + 2 < nsteps) {
+                    if (hq == 0) { tc::mbar_wait(&bar_load[(i + 1) % NLB], (uint32_t)(((i + 1) / NLB) & 1)); if (ts) g_bw2_ts[512 + n * 4 + 0] = clock64(); }
+                    issue_scores(n + 2);
+                    if (ts) g_bw2_ts[512 + n * 4 + 2] = clock64();
+                    tc::mma_commit(&bar_S[s]);
+                }
+                if (ts) g_bw2_ts[n * 8 + 1] = clock64();
+                const uint32_t off = (i % NLB) * TILE_B + hq * 64 * 16;
+                if (!(debug & 16)) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)     // dV[key,d] += P^T[key, 64 q] dO[64 q, d]
+                    tc::mma_bf16(tmem + TM_DV, kPT.adv(s * PT_B + k * KS).u64(), mdO.adv(off + k * tc::KSTEP_MN).u64(), idescKM, (n | k) != 0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)     // dK[key,d] += dS^T[key, 64 q] Q[64 q, d]
+                    tc::mma_bf16(tmem + TM_DK, kdS.adv((i & 1) * DS_B + (hq * 4 + k) * KS).u64(), mQ.adv(off + k * tc::KSTEP_MN).u64(), idescKM, (n | k) != 0);
+                }
+                if (hq == 1 && !(debug & 4)) {
+                    if (i >= 2 && !(debug & 32)) { tc::mbar_wait(&bar_dq[i & 1], (uint32_t)(((i - 2) >> 1) & 1)); tc::fence_after_sync(); }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)   // dQ[q,d] = dS[q, key] K[key, d] over the 128 queries of the tile
+                        tc::mma_bf16(tmem + TM_DQ + (uint32_t)(i & 1) * 32u, mdS.adv((i & 1) * DS_B + k * tc::KSTEP_MN).u64(),
+                                     mK.adv(k * tc::KSTEP_MN).u64(), idescMM, k > 0);
+                }
+                tc::mma_commit(&bar_acc[s]);
+                if (ts) g_bw2_ts[n * 8 + 2] = clock64();
+            }
+        }
+        __syncwarp();
+    } else if (warp >= W_DRAIN) {
+        // ------------------------------------------------------------------ dQ drain: TMEM -> staging -> bulk reduce-add
+        const int quarter = warp & 3;
+        const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
+        float* stg = reinterpret_cast<float*>(sm + OFF_STG + quarter * 4096);
+        for (int i = 0; i < ((debug & 32) ? 0 : nq); ++i) {
+            tc::mbar_wait(&bar_acc[1], (uint32_t)(i & 1));
+            tc::fence_after_sync();
+            float t[32];
+            if (!(debug & 4096)) tc::tmem_ld32(tlane + TM_DQ + (uint32_t)(i & 1) * 32u, t);
+            else { for (int c = 0; c < 32; ++c) t[c] = 0.f; }
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) { tc::mbar_arrive(&bar_dq[i & 1]); tc::bulk_wait_read0(); }   // staging block free again
+            __syncwarp();
+            if (!(debug & 2048)) {
+                // Row `lane` is 128 contiguous bytes (the bulk reduce needs the block linear), so a straight float4 store
+                // would put all lanes of a quarter-warp on the same four banks (8-way conflict, ~1000 smem cycles per
+                // tile that also stall the tensor core's operand reads).  Lane l instead writes its chunks in the order
+                // (j + l) mod 8: the register array is rotated by l with three conditional-move stages.
+                float4 v[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) v[c] = make_float4(t[4 * c] * scale, t[4 * c + 1] * scale, t[4 * c + 2] * scale, t[4 * c + 3] * scale);
+                const int rot = lane & 7;
+#pragma unroll
+                for (int sh = 1; sh < 8; sh <<= 1) {
+                    const bool on = (rot & sh) != 0;
+                    float4 w[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) w[c] = on ? v[(c + sh) & 7] : v[c];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) v[c] = w[c];
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(stg + lane * 32 + ((j + rot) & 7) * 4) = v[j];
+            }
+            if (!(debug & 1024)) tc::fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                const int q0 = i * 128 + quarter * 32;
+                const int rows = min(32, S - q0);
+                if (rows > 0 && !(debug & 1)) tc::bulk_reduce_add_f32(dQacc + head_off + (size_t)q0 * D, stg, (uint32_t)rows * (D * 4));
+                tc::bulk_commit();
+            }
+        }
+        if (lane == 0) tc::bulk_wait0();
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ compute warps
+        const int quarter = warp & 3, cg = warp >> 2;
+        const int row = quarter * 32 + lane, key = k0 + row;
+        const bool valid_k = key < S;
+        const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
+        const int c0 = cg * CPT;
+        const uint32_t kterm = (uint32_t)key * 0x85EBCA6Bu;
+        for (int n = 0; n < nsteps; ++n) {
+            const int i = n >> 1, hq = n & 1, s = n & 1, buf = i % NLB;
+            if (hq == 0) tc::mbar_wait(&bar_load[buf], (uint32_t)((i / NLB) & 1));  // lse / D / row keys of the tile
+            const bool ts = (debug & 512) && blockIdx.x == 0 && blockIdx.y == 0 && n < 32 && warp == 5 && lane == 0;
+            if (ts) g_bw2_ts[n * 8 + 3] = clock64();
+            tc::mbar_wait(&bar_S[s], (uint32_t)((n >> 1) & 1));
+            tc::fence_after_sync();
+            if (ts) g_bw2_ts[n * 8 + 4] = clock64();
+            float st[CPT], dp[CPT];
+            {
+                uint32_t r0[CPT], r1[CPT];
+                if constexpr (CPT == 16) {
+                    tc::tmem_ld16_nowait(tlane + (uint32_t)s * 128u + c0, r0);
+                    tc::tmem_ld16_nowait(tlane + (uint32_t)s * 128u + 64u + c0, r1);
+                } else {
+                    tc::tmem_ld32_nowait(tlane + (uint32_t)s * 128u + c0, r0);
+                    tc::tmem_ld32_nowait(tlane + (uint32_t)s * 128u + 64u + c0, r1);
+                }
+                tc::tmem_wait_ld();
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) { st[c] = __uint_as_float(r0[c]); dp[c] = __uint_as_float(r1[c]); }
+            }
+            if (ts) g_bw2_ts[n * 8 + 5] = clock64();
+            if (!valid_k) {                           // padding keys: exp2(-inf) = 0 -> P = dS = 0
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) st[c] = -INFINITY;
+            }
+            if (!(debug & 8)) {
+            const float* ls_p = &lse_s[buf][hq * 64 + c0];
+            const float* dd_p = &D_s[buf][hq * 64 + c0];
+            const uint32_t* rk_p = &rk_s[buf][hq * 64 + c0];
+            uint4 pk[CPT / 8], dk[CPT / 8];
+#pragma unroll
+            for (int c8 = 0; c8 < CPT / 8; ++c8) {
+                const float4 l0 = *reinterpret_cast<const float4*>(ls_p + c8 * 8);
+                const float4 l1 = *reinterpret_cast<const float4*>(ls_p + c8 * 8 + 4);
+                const float4 d0 = *reinterpret_cast<const float4*>(dd_p + c8 * 8);
+                const float4 d1 = *reinterpret_cast<const float4*>(dd_p + c8 * 8 + 4);
+                const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+                const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+                float p[8], ds[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    p[c] = ex2_approx(fmaf(st[c8 * 8 + c], scale_log2, -ls[c]));
+                    if (DROP) {
+                        const float mk = (lowbias32(rk_p[c8 * 8 + c] ^ kterm) >= dc.thresh) ? dc.inv_keep : 0.f;
+                        ds[c] = p[c] * fmaf(dp[c8 * 8 + c], mk, -dd[c]);
+                        p[c] *= mk;                                       // P^T feeds dV with the dropped probabilities
+                    } else {
+                        ds[c] = p[c] * (dp[c8 * 8 + c] - dd[c]);          // unscaled; `scale` is applied to dQ / dK at the end
+                    }
+                }
+                pk[c8].x = tc::pack_bf16(p[0], p[1]); pk[c8].y = tc::pack_bf16(p[2], p[3]);
+                pk[c8].z = tc::pack_bf16(p[4], p[5]); pk[c8].w = tc::pack_bf16(p[6], p[7]);
+                dk[c8].x = tc::pack_bf16(ds[0], ds[1]); dk[c8].y = tc::pack_bf16(ds[2], ds[3]);
+                dk[c8].z = tc::pack_bf16(ds[4], ds[5]); dk[c8].w = tc::pack_bf16(ds[6], ds[7]);
+            }
+            if (n >= 2) tc::mbar_wait(&bar_acc[s], (uint32_t)(((n >> 1) - 1) & 1));   // dV / dK of step n-2 have read P^T[s]
+            uint8_t* pt = sm + OFF_PT + s * PT_B + (cg * (CPT / 8)) * (128 * 16) + row * 16;
+            uint8_t* dst = sm + OFF_DS + (i & 1) * DS_B + (hq * 8 + cg * (CPT / 8)) * (128 * 16) + row * 16;
+#pragma unroll
+            for (int c8 = 0; c8 < CPT / 8; ++c8) {
+                *reinterpret_cast<uint4*>(pt + c8 * (128 * 16)) = pk[c8];
+                *reinterpret_cast<uint4*>(dst + c8 * (128 * 16)) = dk[c8];
+            }
+            }
+            if (ts) g_bw2_ts[n * 8 + 6] = clock64();
+            if (!(debug & 64)) tc::fence_async_smem();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&bar_cmp[s]);
+            if (ts) g_bw2_ts[n * 8 + 7] = clock64();
+        }
+        // ---- epilogue: dK (scaled), dV of this key tile ----
+        tc::mbar_wait(&bar_acc[1], (uint32_t)(((nsteps - 1) >> 1) & 1));
+        tc::fence_after_sync();
+        if constexpr (CQ == 8) {
+            float t[8];
+            tc::tmem_ld8(tlane + TM_DK + cg * 8, t);
+            if (valid_k) {
+                float* dkp = dKh + head_off + (size_t)key * D + cg * 8;
+                *reinterpret_cast<float4*>(dkp) = make_float4(t[0] * scale, t[1] * scale, t[2] * scale, t[3] * scale);
+                *reinterpret_cast<float4*>(dkp + 4) = make_float4(t[4] * scale, t[5] * scale, t[6] * scale, t[7] * scale);
+            }
+            tc::tmem_ld8(tlane + TM_DV + cg * 8, t);
+            if (valid_k) {
+                float* dvp = dVh + head_off + (size_t)key * D + cg * 8;
+                *reinterpret_cast<float4*>(dvp) = make_float4(t[0], t[1], t[2], t[3]);
+                *reinterpret_cast<float4*>(dvp + 4) = make_float4(t[4], t[5], t[6], t[7]);
+            }
+        } else {
+            float t[16];
+            tc::tmem_ld16(tlane + TM_DK + cg * 16, t);
+            if (valid_k) {
+                float* dkp = dKh + head_off + (size_t)key * D + cg * 16;
+#pragma unroll
+                for (int c = 0; c < 16; c += 4)
+                    *reinterpret_cast<float4*>(dkp + c) = make_float4(t[c] * scale, t[c + 1] * scale, t[c + 2] * scale, t[c + 3] * scale);
+            }
+            tc::tmem_ld16(tlane + TM_DV + cg * 16, t);
+            if (valid_k) {
+                float* dvp = dVh + head_off + (size_t)key * D + cg * 16;
+#pragma unroll
+                for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(dvp + c) = make_float4(t[c], t[c + 1], t[c + 2], t[c + 3]);
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
 // --------------------------------------------------------------------------- host side
 struct AttnWs {
     bf16 *Qb, *Kb, *Vb, *dOb;
     float *Dvec, *dQacc, *dKh, *dVh;
 };
 static size_t attn_ws_bytes(int64_t B, int64_t S, int H, int Hkv, int d) {
-    const size_t qe = (size_t)B * H * S * d, ke = (size_t)B * Hkv * S * d;
-    return align_up(qe * 2) * 2 + align_up(ke * 2) * 2 + align_up((size_t)B * H * S * 4) + 3 * align_up(qe * 4) + 1024;
+    const size_t qe = (size_t)B * H * S * d, ke = (size_t)B * Hkv * S * d, qp = (size_t)B * H * pad128(S) * d;
+    return align_up(qp * 2) * 2 + align_up(ke * 2) * 2 + align_up((size_t)B * H * S * 4) + 3 * align_up(qe * 4) + 1024;
 }
 static bool attn_carve(AttnWs& w, void* ws, size_t bytes, int64_t B, int64_t S, int H, int Hkv, int d) {
     Arena ar(ws, bytes);
-    const size_t qe = (size_t)B * H * S * d, ke = (size_t)B * Hkv * S * d;
-    w.Qb = ar.take<bf16>(qe); w.Kb = ar.take<bf16>(ke); w.Vb = ar.take<bf16>(ke); w.dOb = ar.take<bf16>(qe);
+    const size_t qe = (size_t)B * H * S * d, ke = (size_t)B * Hkv * S * d, qp = (size_t)B * H * pad128(S) * d;
+    w.Qb = ar.take<bf16>(qp); w.Kb = ar.take<bf16>(ke); w.Vb = ar.take<bf16>(ke); w.dOb = ar.take<bf16>(qp);
     w.Dvec = ar.take<float>((size_t)B * H * S);
     w.dQacc = ar.take<float>(qe); w.dKh = ar.take<float>(qe); w.dVh = ar.take<float>(qe);
     return ar.ok();
@@ -734,11 +1107,11 @@ static inline unsigned nb256(int64_t n) { return (unsigned)((n + 255) / 256); }
 
 static int attn_prep_all(const float* q, const float* k, const float* v, const AttnWs& w, int64_t B, int64_t S,
                          int H, int Hkv, int d, const float* freqs, cudaStream_t st) {
-    attn_prep_kernel<<<nb256(B * S * H * (d / 8)), 256, 0, st>>>(q, w.Qb, B, S, H, d, freqs);
+    attn_prep_kernel<<<nb256(B * pad128(S) * H * (d / 8)), 256, 0, st>>>(q, w.Qb, B, S, H, d, freqs, 1);
     GAOT_LAUNCH_CHECK();
-    attn_prep_kernel<<<nb256(B * S * Hkv * (d / 8)), 256, 0, st>>>(k, w.Kb, B, S, Hkv, d, freqs);
+    attn_prep_kernel<<<nb256(B * S * Hkv * (d / 8)), 256, 0, st>>>(k, w.Kb, B, S, Hkv, d, freqs, 0);
     GAOT_LAUNCH_CHECK();
-    attn_prep_kernel<<<nb256(B * S * Hkv * (d / 8)), 256, 0, st>>>(v, w.Vb, B, S, Hkv, d, nullptr);
+    attn_prep_kernel<<<nb256(B * S * Hkv * (d / 8)), 256, 0, st>>>(v, w.Vb, B, S, Hkv, d, nullptr, 0);
     GAOT_LAUNCH_CHECK();
     return GAOT_OK;
 }
@@ -748,6 +1121,10 @@ static int attn_prep_all(const float* q, const float* k, const float* v, const A
 using namespace gaot;
 
 extern "C" {
+
+int gaot_debug_bw2_timestamps(long long* host, int n) {
+    return cudaMemcpyFromSymbol(host, g_bw2_ts, sizeof(long long) * (size_t)(n < 1024 ? n : 1024)) == cudaSuccess ? 0 : 1;
+}
 
 size_t gaot_attn_workspace_bytes(int64_t B, int64_t S, int32_t H, int32_t Hkv, int32_t d) {
     return attn_ws_bytes(B, S, H, Hkv, d);
@@ -769,11 +1146,13 @@ static int attn_launch_fwd(const AttnWs& w, int64_t B, int64_t S, int H, int Hkv
     const float scale_log2 = (1.0f / sqrtf((float)d)) * 1.4426950408889634f;
     const DropCfg dc = make_drop(dropout_p, seed);
     const bool drop = dropout_p > 0.f;
+    const char* dbg_env = getenv("GAOT_ATTN_DEBUG");
+    const int dbg = dbg_env ? atoi(dbg_env) : 0;
     dim3 grid((unsigned)((S + 127) / 128), (unsigned)H, (unsigned)B);
     GAOT_TIME_KERNEL("attn_fwd", st, 4.0 * (double)B * H * (double)S * (double)S * d);
 #define GAOT_FWD_LAUNCH(DD, DR, SM)                                                                                   \
     do { GAOT_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DD, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM))); \
-         attn_fwd_kernel<DD, DR><<<grid, 128, (SM), st>>>(w.Qb, w.Kb, w.Vb, out, out_bf16, out32, lse, (int)S, H, Hkv, scale_log2, dc); } while (0)
+         attn_fwd_kernel<DD, DR><<<grid, 128, (SM), st>>>(w.Qb, w.Kb, w.Vb, out, out_bf16, out32, lse, (int)S, H, Hkv, scale_log2, dbg, dc); } while (0)
     if (d == 32) {
         const size_t smem = 3 * 128 * 32 * 2 + 2 * 128 * 48 * 2 + 128 * 128 * 2;
         if (drop) GAOT_FWD_LAUNCH(32, true, smem); else GAOT_FWD_LAUNCH(32, false, smem);
@@ -810,6 +1189,18 @@ static int attn_launch_bwd(const AttnWs& w, const float* lse, int64_t B, int64_t
     GAOT_TIME_KERNEL("attn_bwd", st, 10.0 * (double)B * H * (double)S * (double)S * d);
     const DropCfg dc = make_drop(dropout_p, seed);
     const bool drop = dropout_p > 0.f;
+    if (d == 32 && !(dbg & 128)) {                   // warp-specialised kernel (GAOT_ATTN_DEBUG bit 7 selects the older one)
+        const int ncw = (dbg & 256) ? 8 : 16;
+#define GAOT_BWD2_LAUNCH(NCW, DR)                                                                                      \
+    do { GAOT_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<NCW, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bw2::SMEM)); \
+         attn_bwd2_kernel<NCW, DR><<<grid, (NCW + 6) * 32, bw2::SMEM, st>>>(w.Qb, w.Kb, w.Vb, w.dOb, lse, w.Dvec, w.dQacc, w.dKh, w.dVh, \
+                                                                           (int)S, H, Hkv, scale, scale_log2, dbg, dc); } while (0)
+        if (ncw == 16) { if (drop) GAOT_BWD2_LAUNCH(16, true); else GAOT_BWD2_LAUNCH(16, false); }
+        else           { if (drop) GAOT_BWD2_LAUNCH(8, true);  else GAOT_BWD2_LAUNCH(8, false); }
+#undef GAOT_BWD2_LAUNCH
+        GAOT_LAUNCH_CHECK();
+        return GAOT_OK;
+    }
 #define GAOT_BWD_LAUNCH(DD, DR, SM)                                                                                   \
     do { GAOT_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<DD, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM))); \
          attn_bwd_kernel<DD, DR><<<grid, 256, (SM), st>>>(w.Qb, w.Kb, w.Vb, w.dOb, lse, w.Dvec, w.dQacc, w.dKh, w.dVh,    \
@@ -837,7 +1228,7 @@ int gaot_attn_backward(const float* q, const float* k, const float* v, const flo
     if (!attn_carve(w, ws, ws_bytes, B, S, H, Hkv, d)) { set_error("attn_backward: workspace too small"); return GAOT_ERR_WORKSPACE; }
     rc = attn_prep_all(q, k, v, w, B, S, H, Hkv, d, rope_freqs, st);
     if (rc) return rc;
-    attn_bwd_prep_kernel<<<nb256(B * S * H), 256, 0, st>>>(d_out, out, w.dOb, w.Dvec, B, S, H, d);
+    attn_bwd_prep_kernel<<<nb256(B * pad128(S) * H), 256, 0, st>>>(d_out, out, w.dOb, w.Dvec, B, S, H, d);
     GAOT_LAUNCH_CHECK();
     rc = attn_launch_bwd(w, lse, B, S, H, Hkv, d, dropout_p, seed, st);
     if (rc) return rc;
@@ -852,12 +1243,12 @@ int gaot_attn_backward(const float* q, const float* k, const float* v, const flo
 
 // ---- fused-block flavour: operands stay in the kernels' own bf16 per-head layout between forward and backward ----
 size_t gaot_attn_packed_bytes(int64_t B, int64_t S, int32_t H, int32_t Hkv, int32_t d) {
-    return align_up((size_t)B * H * S * d * 2) + 2 * align_up((size_t)B * Hkv * S * d * 2);
+    return align_up((size_t)B * H * pad128(S) * d * 2) + 2 * align_up((size_t)B * Hkv * S * d * 2);
 }
 
 static void attn_packed_ptrs(AttnWs& w, void* packed, int64_t B, int64_t S, int H, int Hkv, int d) {
     char* p = (char*)packed;
-    w.Qb = (bf16*)p; p += align_up((size_t)B * H * S * d * 2);
+    w.Qb = (bf16*)p; p += align_up((size_t)B * H * pad128(S) * d * 2);
     w.Kb = (bf16*)p; p += align_up((size_t)B * Hkv * S * d * 2);
     w.Vb = (bf16*)p;
 }
@@ -871,14 +1262,14 @@ int gaot_attn_fused_forward(const void* qkv, int64_t ld, int64_t B, int64_t S, i
     GAOT_CHECK_ARG(qkv && packed && out && out_f32 && lse && ld % 8 == 0, "attn_fused_forward: bad pointer / ld");
     AttnWs w{};
     attn_packed_ptrs(w, packed, B, S, H, Hkv, d);
-    attn_pack_qkv_kernel<<<nb256(B * S * (H + 2 * Hkv) * (d / 8)), 256, 0, st>>>((const bf16*)qkv, ld, w.Qb, w.Kb, w.Vb, B, S, H, Hkv, d, rope_freqs);
+    attn_pack_qkv_kernel<<<nb256(B * pad128(S) * (H + 2 * Hkv) * (d / 8)), 256, 0, st>>>((const bf16*)qkv, ld, w.Qb, w.Kb, w.Vb, B, S, H, Hkv, d, rope_freqs);
     GAOT_LAUNCH_CHECK();
     return attn_launch_fwd(w, B, S, H, Hkv, d, dropout_p, seed, out, 1, out_f32, lse, st);
 }
 
 size_t gaot_attn_fused_backward_workspace_bytes(int64_t B, int64_t S, int32_t H, int32_t d) {
-    const size_t qe = (size_t)B * H * S * d;
-    return align_up(qe * 2) + align_up((size_t)B * H * S * 4) + 3 * align_up(qe * 4) + 1024;
+    const size_t qe = (size_t)B * H * S * d, qp = (size_t)B * H * pad128(S) * d;
+    return align_up(qp * 2) + align_up((size_t)B * H * S * 4) + 3 * align_up(qe * 4) + 1024;
 }
 
 int gaot_attn_fused_backward(const void* packed, const float* out, const void* d_out, const float* lse,
@@ -892,11 +1283,11 @@ int gaot_attn_fused_backward(const void* packed, const float* out, const void* d
     AttnWs w{};
     attn_packed_ptrs(w, const_cast<void*>(packed), B, S, H, Hkv, d);
     Arena ar(ws, ws_bytes);
-    const size_t qe = (size_t)B * H * S * d;
-    w.dOb = ar.take<bf16>(qe); w.Dvec = ar.take<float>((size_t)B * H * S);
+    const size_t qe = (size_t)B * H * S * d, qp = (size_t)B * H * pad128(S) * d;
+    w.dOb = ar.take<bf16>(qp); w.Dvec = ar.take<float>((size_t)B * H * S);
     w.dQacc = ar.take<float>(qe); w.dKh = ar.take<float>(qe); w.dVh = ar.take<float>(qe);
     if (!ar.ok()) { set_error("attn_fused_backward: workspace too small"); return GAOT_ERR_WORKSPACE; }
-    attn_bwd_prep_bf16_kernel<<<nb256(B * S * H), 256, 0, st>>>((const bf16*)d_out, out, w.dOb, w.Dvec, B, S, H, d);
+    attn_bwd_prep_bf16_kernel<<<nb256(B * pad128(S) * H), 256, 0, st>>>((const bf16*)d_out, out, w.dOb, w.Dvec, B, S, H, d);
     GAOT_LAUNCH_CHECK();
     rc = attn_launch_bwd(w, lse, B, S, H, Hkv, d, dropout_p, seed, st);
     if (rc) return rc;

@@ -18,7 +18,7 @@ def relerr(a, b):
 
 
 @pytest.mark.parametrize("B,S,H,Hkv,d,rope", [(1, 512, 8, 8, 32, True), (2, 200, 4, 2, 32, True), (1, 384, 2, 2, 64, False),
-                                                (1, 1024, 8, 8, 32, False), (1, 129, 2, 1, 32, True)])
+                                                (1, 1024, 8, 8, 32, False), (1, 129, 2, 1, 32, True), (1, 2300, 2, 1, 32, True)])
 def test_attention_vs_oracle(B, S, H, Hkv, d, rope):
     from gaot_3d_b200 import ops
     from gaot_3d_b200.layers.attn import RotaryEmbedding
@@ -59,7 +59,7 @@ def test_attention_module_golden(tag):
             assert l2 < 1.5e-2, (n, l2, mx)
 
 
-@pytest.mark.parametrize("B,S,H,Hkv,d,p", [(1, 384, 4, 4, 32, 0.1), (2, 200, 4, 2, 32, 0.3)])
+@pytest.mark.parametrize("B,S,H,Hkv,d,p", [(1, 384, 4, 4, 32, 0.1), (2, 200, 4, 2, 32, 0.3), (1, 1100, 2, 2, 32, 0.2)])
 def test_attention_dropout_matches_oracle_mask(B, S, H, Hkv, d, p):
     """Training-mode dropout (reference attn.py:122-126): the kernels' counter-based mask is restated in
     oracle.attn.dropout_keep, so forward and backward are checked exactly like the p=0 case."""
