@@ -27,11 +27,22 @@ using bf16 = __nv_bfloat16;
 // --------------------------------------------------------------------------- operand layouts
 // K and V stay row-major bf16 [B,Hkv,S,d].  Q and dO are stored PRE-TILED: per (b,h) ceil(S/128) tiles of 128 rows, each
 // tile already in the kernels' chunk-major shared-memory layout (tc05.cuh: 16-byte chunk c of row r at c*128*16 + r*16),
-// rows >= S zero.  A tile is therefore one contiguous 128*d*2-byte block that the backward's loader moves with a single
-// cp.async.bulk (TMA engine, async proxy: no generic->async proxy fence in front of the tensor core).
+// rows >= S zero.  A tile is one contiguous block that the backward's loader moves with a single cp.async.bulk (TMA
+// engine, async proxy: no generic->async proxy fence in front of the tensor core).
+// Two further conventions let the backward's tensor core produce the softmax arguments directly:
+//   * Q is stored multiplied by (1/sqrt(d)) * log2(e), so S = Q K^T is already in the scaled log2 domain;
+//   * every tile carries ONE extra chunk (index d/8) per row: for Q it holds (-lse_hi, -lse_lo, 0...), for dO
+//     (-D_hi, -D_lo, 0...) as bf16 hi/lo pairs, written by the backward prep kernel.  With K and V extended by a chunk
+//     (1, 1, 0...) the products K' Q'^T = S - lse and V' dO'^T = dP - D need no per-element correction.
 __host__ __device__ __forceinline__ int64_t pad128(int64_t S) { return (S + 127) / 128 * 128; }
+__host__ __device__ __forceinline__ int64_t tile_elems(int d) { return 128 * (int64_t)(d + 8); }
 __device__ __forceinline__ size_t tiled_off(int64_t head, int64_t S_pad, int64_t s, int d, int ch) {
-    return ((size_t)head * S_pad + (size_t)(s & ~(int64_t)127)) * d + (size_t)ch * (128 * 8) + (size_t)(s & 127) * 8;
+    return ((size_t)head * (S_pad >> 7) + (size_t)(s >> 7)) * tile_elems(d) + (size_t)ch * (128 * 8) + (size_t)(s & 127) * 8;
+}
+__device__ __forceinline__ uint4 hilo_chunk(float x) {        // bf16 (hi, lo) split of x, rest of the chunk zero
+    const bf16 hi = __float2bfloat16_rn(x);
+    const bf16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+    return make_uint4((uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16), 0u, 0u, 0u);
 }
 
 // --------------------------------------------------------------------------- prep kernels
@@ -53,7 +64,7 @@ __device__ __forceinline__ void rope8(float (&x)[8], int s, int c0, const float*
 
 __global__ void __launch_bounds__(256)
 attn_prep_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t B, int64_t S, int nh, int d,
-                 const float* __restrict__ freqs /* NULL: no rope */, int tiled) {
+                 const float* __restrict__ freqs /* NULL: no rope */, int tiled, float qscale) {
     const int cpr = d >> 3;                                   // 8-element chunks per head row
     const int64_t Sx = tiled ? pad128(S) : S;
     const int64_t total = B * Sx * nh * cpr;
@@ -69,6 +80,8 @@ attn_prep_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t 
         const float4 v0 = *reinterpret_cast<const float4*>(p), v1 = *reinterpret_cast<const float4*>(p + 4);
         float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
         if (freqs) rope8<true>(x, (int)s, ch * 8, freqs, false);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] *= qscale;
         o.x = tc::pack_bf16(x[0], x[1]); o.y = tc::pack_bf16(x[2], x[3]);
         o.z = tc::pack_bf16(x[4], x[5]); o.w = tc::pack_bf16(x[6], x[7]);
     }
@@ -85,7 +98,7 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& v, float (&f)[8]) {
 }
 __global__ void __launch_bounds__(256)
 attn_pack_qkv_kernel(const bf16* __restrict__ qkv, int64_t ld, bf16* __restrict__ Qb, bf16* __restrict__ Kb,
-                     bf16* __restrict__ Vb, int64_t B, int64_t S, int H, int Hkv, int d, const float* __restrict__ freqs) {
+                     bf16* __restrict__ Vb, int64_t B, int64_t S, int H, int Hkv, int d, const float* __restrict__ freqs, float qscale) {
     const int cpr = d >> 3, nh = H + 2 * Hkv;
     const int64_t Sp = pad128(S);
     const int64_t total = B * Sp * nh * cpr;
@@ -105,10 +118,14 @@ attn_pack_qkv_kernel(const bf16* __restrict__ qkv, int64_t ld, bf16* __restrict_
     else if (hh < H + Hkv) { dst = Kb + ((b * Hkv + (hh - H)) * S + s) * d + ch * 8; rope = true; }
     else { dst = Vb + ((b * Hkv + (hh - H - Hkv)) * S + s) * d + ch * 8; rope = false; }
     uint4 o = raw;
-    if (rope && freqs) {
+    if ((rope && freqs) || hh < H) {
         float x[8];
         unpack_bf16x8(raw, x);
-        rope8<true>(x, (int)s, ch * 8, freqs, false);
+        if (rope && freqs) rope8<true>(x, (int)s, ch * 8, freqs, false);
+        if (hh < H) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] *= qscale;
+        }
         o.x = tc::pack_bf16(x[0], x[1]); o.y = tc::pack_bf16(x[2], x[3]);
         o.z = tc::pack_bf16(x[4], x[5]); o.w = tc::pack_bf16(x[6], x[7]);
     }
@@ -121,15 +138,18 @@ attn_pack_qkv_kernel(const bf16* __restrict__ qkv, int64_t ld, bf16* __restrict_
 // swamps dQ / dK wherever the attention is close to uniform.
 __global__ void __launch_bounds__(256)
 attn_bwd_prep_bf16_kernel(const bf16* __restrict__ dO, const float* __restrict__ O, bf16* __restrict__ dOb,
-                          float* __restrict__ Dvec, int64_t B, int64_t S, int H, int d) {
+                          float* __restrict__ Dvec, bf16* __restrict__ Qb, const float* __restrict__ lse, int fold_D,
+                          int64_t B, int64_t S, int H, int d) {
     const int64_t Sp = pad128(S);
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // (b, s, h) over the padded length
     if (idx >= B * Sp * H) return;
     const int h = (int)(idx % H);
     const int64_t s = (idx / H) % Sp, b = idx / ((int64_t)H * Sp);
     bf16* out = dOb + tiled_off(b * H + h, Sp, s, d, 0);
+    bf16* qx = Qb + tiled_off(b * H + h, Sp, s, d, d >> 3);            // the tile's extra chunk of this row
     if (s >= S) {
-        for (int c = 0; c < d; c += 8) *reinterpret_cast<uint4*>(out + (c >> 3) * (128 * 8)) = make_uint4(0u, 0u, 0u, 0u);
+        for (int c = 0; c <= d; c += 8) *reinterpret_cast<uint4*>(out + (c >> 3) * (128 * 8)) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(qx) = make_uint4(0u, 0u, 0u, 0u);
         return;
     }
     const bf16* pd = dO + ((b * S + s) * H + h) * d;
@@ -144,6 +164,8 @@ attn_bwd_prep_bf16_kernel(const bf16* __restrict__ dO, const float* __restrict__
         *reinterpret_cast<uint4*>(out + (c >> 3) * (128 * 8)) = a;
     }
     Dvec[(b * H + h) * S + s] = acc;
+    *reinterpret_cast<uint4*>(out + (d >> 3) * (128 * 8)) = fold_D ? hilo_chunk(-acc) : make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(qx) = hilo_chunk(-lse[(b * H + h) * S + s]);
 }
 
 // fused-block backward post: per-head fp32 dQ / dK / dV -> ONE bf16 token-major [B*S, ld] gradient of the fused
@@ -180,15 +202,18 @@ attn_bwd_post_qkv_kernel(const float* __restrict__ dQh, const float* __restrict_
 // backward prep: dO -> bf16 [B,H,S,d] and Dvec[b,h,s] = sum_c dO*O
 __global__ void __launch_bounds__(256)
 attn_bwd_prep_kernel(const float* __restrict__ dO, const float* __restrict__ O, bf16* __restrict__ dOb,
-                     float* __restrict__ Dvec, int64_t B, int64_t S, int H, int d) {
+                     float* __restrict__ Dvec, bf16* __restrict__ Qb, const float* __restrict__ lse, int fold_D,
+                          int64_t B, int64_t S, int H, int d) {
     const int64_t Sp = pad128(S);
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // (b, s, h) over the padded length
     if (idx >= B * Sp * H) return;
     const int h = (int)(idx % H);
     const int64_t s = (idx / H) % Sp, b = idx / ((int64_t)H * Sp);
     bf16* out = dOb + tiled_off(b * H + h, Sp, s, d, 0);
+    bf16* qx = Qb + tiled_off(b * H + h, Sp, s, d, d >> 3);            // the tile's extra chunk of this row
     if (s >= S) {
-        for (int c = 0; c < d; c += 8) *reinterpret_cast<uint4*>(out + (c >> 3) * (128 * 8)) = make_uint4(0u, 0u, 0u, 0u);
+        for (int c = 0; c <= d; c += 8) *reinterpret_cast<uint4*>(out + (c >> 3) * (128 * 8)) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(qx) = make_uint4(0u, 0u, 0u, 0u);
         return;
     }
     const float* pd = dO + ((b * S + s) * H + h) * d;
@@ -204,6 +229,8 @@ attn_bwd_prep_kernel(const float* __restrict__ dO, const float* __restrict__ O, 
         *reinterpret_cast<uint4*>(out + (c >> 3) * (128 * 8)) = o;
     }
     Dvec[(b * H + h) * S + s] = acc;
+    *reinterpret_cast<uint4*>(out + (d >> 3) * (128 * 8)) = fold_D ? hilo_chunk(-acc) : make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(qx) = hilo_chunk(-lse[(b * H + h) * S + s]);
 }
 
 // backward post: [B,H,S,d] fp32 per-head grads -> token-major [B,S,nh_out*d], summing the GQA group
@@ -242,7 +269,7 @@ __device__ __forceinline__ void load_row(const bf16* __restrict__ g, bool valid,
 // row `s` of a pre-tiled operand (head base `g`, see tiled_off)
 template <int D>
 __device__ __forceinline__ void load_row_tiled(const bf16* __restrict__ g, int64_t s, bool valid, uint4 (&r)[D / 8]) {
-    const bf16* p = g + (size_t)(s & ~(int64_t)127) * D + (size_t)(s & 127) * 8;
+    const bf16* p = g + (size_t)(s >> 7) * tile_elems(D) + (size_t)(s & 127) * 8;
 #pragma unroll
     for (int c = 0; c < D / 8; ++c)
         r[c] = valid ? *reinterpret_cast<const uint4*>(p + c * (128 * 8)) : make_uint4(0u, 0u, 0u, 0u);
@@ -313,7 +340,7 @@ attn_fwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
     uint4 kreg[D / 8], vreg[D / 8];                     // register-staged K/V rows of a future tile
     {
         uint4 r[D / 8];
-        load_row_tiled<D>(Qb + (size_t)(b * H + h) * pad128(S) * D, valid_q ? q : 0, valid_q, r);
+        load_row_tiled<D>(Qb + (size_t)(b * H + h) * (pad128(S) >> 7) * tile_elems(D), valid_q ? q : 0, valid_q, r);
         store_row<D>(Qs, tid, r);
         const bool vk = tid < S;
         load_row<D>(Kbase + (size_t)(vk ? tid : 0) * D, vk, r);
@@ -506,7 +533,7 @@ __global__ void __launch_bounds__(256, 2)
 attn_bwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const bf16* __restrict__ Vb,
                 const bf16* __restrict__ dOb, const float* __restrict__ lse, const float* __restrict__ Dvec,
                 float* __restrict__ dQacc, float* __restrict__ dKh, float* __restrict__ dVh,
-                int S, int H, int Hkv, float scale, float scale_log2, int debug, const DropCfg dc) {
+                int S, int H, int Hkv, float scale, float scale_dk, float scale_log2, int debug, const DropCfg dc) {
     extern __shared__ __align__(1024) uint8_t sm[];
     __shared__ uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
@@ -531,7 +558,7 @@ attn_bwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
     const size_t stat_off = ((size_t)b * H + h) * S;
     const int nq = (S + 127) / 128;
     constexpr uint32_t TM_ST = 0, TM_DPT = 64, TM_DV = 128, TM_DK = 128 + D, TM_DQ = 128 + 2 * D;
-    const bf16* tile_src = (half == 0 ? Qb : dOb) + (size_t)(b * H + h) * pad128(S) * D;   // pre-tiled operands
+    const bf16* tile_src = (half == 0 ? Qb : dOb) + (size_t)(b * H + h) * (pad128(S) >> 7) * tile_elems(D);   // pre-tiled operands
     const float* stat_src = (half == 0 ? lse : Dvec) + stat_off;
 
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, TM_COLS);
@@ -737,7 +764,7 @@ attn_bwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
         if constexpr (D == 32) tc::tmem_ld16(tlane + TM_DK + half * 16, t);
         else tc::tmem_ld32(tlane + TM_DK + half * 32, t);
         if (valid_k) for (int c = 0; c < D / 2; c += 4)
-            *reinterpret_cast<float4*>(dk + c) = make_float4(t[c] * scale, t[c + 1] * scale, t[c + 2] * scale, t[c + 3] * scale);
+            *reinterpret_cast<float4*>(dk + c) = make_float4(t[c] * scale_dk, t[c + 1] * scale_dk, t[c + 2] * scale_dk, t[c + 3] * scale_dk);
         if constexpr (D == 32) tc::tmem_ld16(tlane + TM_DV + half * 16, t);
         else tc::tmem_ld32(tlane + TM_DV + half * 32, t);
         if (valid_k) for (int c = 0; c < D / 2; c += 4)
@@ -753,34 +780,38 @@ attn_bwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
 // in one of TWO TMEM stages, so the tensor core computes the scores of step n+2 while the compute warps are busy with
 // step n+1, and the accumulator products of step n (dV, dK, dQ) drain behind them.  Nothing in the loop is a CTA-wide
 // barrier; the roles talk through mbarriers:
-//   compute warps (16): wait scores(n) -> tcgen05.ld S^T, dP^T (16 columns each) -> P^T = exp2(S^T c - lse),
-//                       dS^T = P^T (dP^T - D) -> bf16 chunk-major tiles -> arrive(cmp[n&1])
+//   compute warps (16): wait scores(n) -> tcgen05.ld S'^T, dP'^T (16 columns each) -> P^T = exp2(S'^T),
+//                       dS^T = P^T dP'^T -> bf16 chunk-major tiles -> arrive(cmp[n&1])
 //   MMA warp (1 lane) : wait cmp[n&1] -> scores(n+2) into the stage just read -> commit(S[n&1]);
 //                       dV += P^T dO, dK += dS^T Q, (second half) dQ = dS K -> commit(acc[n&1])
 //   drain warps (4)   : wait acc of a tile's second step -> tcgen05.ld dQ (128 queries x 32) -> arrive(dq) -> scaled rows
 //                       to a linear 4 KB staging block -> ONE cp.reduce.async.bulk (.add.f32) per warp into global dQ
-//   loader warp (1)   : Q / dO tiles (cp.async, 16-byte chunks scattered into the chunk-major layout) and lse / D / dropout
-//                       row keys, three tiles deep, released by the accumulator barrier of the tile that used the buffer
-// TMEM (512 columns): stage s: S^T at 128 s, dP^T at 128 s + 64; dV 256; dK 288; dQ (two tiles in flight) 320 + 32 b.
-__device__ long long g_bw2_ts[1024];
+//   loader warp (1)   : one cp.async.bulk per pre-tiled Q / dO tile (10 KB each), three tiles deep, released by the
+//                       accumulator barrier of the tile that used the buffer
+// The operands carry the softmax statistics (see "operand layouts"): S' = K'Q'^T = scaled scores - lse and
+// dP' = V'dO'^T = dP - D come out of the tensor core (contraction length 48 = 32 + one hi/lo chunk + a zero chunk), so
+// an element costs one ex2, one multiply and two halves of a pack.  With dropout D is subtracted by hand (dO' carries
+// zeros) because the mask multiplies dP first.
+// TMEM (512 columns): stage s: S'^T at 128 s, dP'^T at 128 s + 64; dV 256; dK 288; dQ (two tiles in flight) 320 + 32 b.
 namespace bw2 {
 constexpr int D = 32;
-constexpr int TILE_B = 128 * D * 2;                 // 8 KB: one 128-row x 32 bf16 tile
+constexpr int NLB = 3;                              // Q / dO tile buffers
+constexpr int TILE_B = 128 * (D + 16) * 2;          // 12 KB: 128 rows x (32 + extra chunk + zero chunk) bf16
+constexpr int TILE_G = 128 * (D + 8) * 2;           // 10 KB: what a tile occupies in global memory (no zero chunk)
 constexpr int PT_B = 128 * 64 * 2;                  // 16 KB: P^T of one step
 constexpr int DS_B = 128 * 128 * 2;                 // 32 KB: dS^T of one query tile
-constexpr int NLB = 4;                              // Q / dO tile buffers
 constexpr int OFF_K = 0, OFF_V = TILE_B, OFF_Q = 2 * TILE_B, OFF_DO = (2 + NLB) * TILE_B, OFF_PT = (2 + 2 * NLB) * TILE_B;
 constexpr int OFF_DS = OFF_PT + 2 * PT_B, OFF_STG = OFF_DS + 2 * DS_B;
-constexpr int SMEM = OFF_STG + 4 * 4096;            // 196608 B
+constexpr int SMEM = OFF_STG + 4 * 4096;            // 212992 B
 constexpr uint32_t TM_DV = 256, TM_DK = 288, TM_DQ = 320;
 }
 
 template <int NCW, bool DROP>
 __global__ void __launch_bounds__((NCW + 6) * 32, 1)
 attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const bf16* __restrict__ Vb,
-                 const bf16* __restrict__ dOb, const float* __restrict__ lse, const float* __restrict__ Dvec,
+                 const bf16* __restrict__ dOb, const float* __restrict__ Dvec,
                  float* __restrict__ dQacc, float* __restrict__ dKh, float* __restrict__ dVh,
-                 int S, int H, int Hkv, float scale, float scale_log2, int debug, const DropCfg dc) {
+                 int S, int H, int Hkv, float scale, float scale_dk, const DropCfg dc) {
     using namespace bw2;
     constexpr int CG = NCW / 4;                      // column groups of a 64-query step
     constexpr int CPT = 64 / CG;                     // score columns per compute thread (16 or 32)
@@ -789,9 +820,8 @@ attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const
     extern __shared__ __align__(1024) uint8_t sm[];
     __shared__ uint64_t bar_S[2], bar_acc[2], bar_cmp[2], bar_load[NLB], bar_dq[2];
     __shared__ uint32_t tmem_base_s;
-    __shared__ __align__(16) float lse_s[NLB][128];    // zero-filled for padding queries (see the loader)
-    __shared__ __align__(16) float D_s[NLB][128];
-    __shared__ __align__(16) uint32_t rk_s[NLB][128];  // DROP: per-query row keys
+    __shared__ __align__(16) float D_s[DROP ? NLB : 1][128];       // DROP only (zero-filled for padding queries)
+    __shared__ __align__(16) uint32_t rk_s[DROP ? NLB : 1][128];   // DROP only: per-query row keys
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * 128;
     const int kvh = h / (H / Hkv);
@@ -806,15 +836,23 @@ attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const
             tc::mbar_init(&bar_S[i], 1); tc::mbar_init(&bar_acc[i], 1); tc::mbar_init(&bar_cmp[i], NCW); tc::mbar_init(&bar_dq[i], 4);
         }
 #pragma unroll
-        for (int i = 0; i < NLB; ++i) tc::mbar_init(&bar_load[i], DROP ? 34 : 33);
+        for (int i = 0; i < NLB; ++i) tc::mbar_init(&bar_load[i], DROP ? 34 : 1);
         tc::mbar_fence_init();
     }
-    if (tid < 256) {                                  // K / V tiles of this CTA (resident for the whole kernel)
+    if (tid < 256) {                                  // K' / V' tiles of this CTA (resident for the whole kernel)
         const int row = tid & 127, which = tid >> 7;
         const bool vk = k0 + row < S;
         uint4 r[D / 8];
         load_row<D>((which == 0 ? Kb : Vb) + ((size_t)(b * Hkv + kvh) * S + (vk ? k0 + row : 0)) * D, vk, r);
-        store_row<D>(sm + (which == 0 ? OFF_K : OFF_V), row, r);
+        uint8_t* tile = sm + (which == 0 ? OFF_K : OFF_V);
+        store_row<D>(tile, row, r);
+        *reinterpret_cast<uint4*>(tile + 4 * (128 * 16) + row * 16) = make_uint4(0x3F803F80u, 0u, 0u, 0u);   // (1, 1, 0...)
+        *reinterpret_cast<uint4*>(tile + 5 * (128 * 16) + row * 16) = make_uint4(0u, 0u, 0u, 0u);
+    } else if (tid < 256 + 128 * 2) {                 // the zero chunk of every Q' / dO' buffer (never overwritten)
+        const int row = tid & 127, which = (tid - 256) >> 7;
+#pragma unroll
+        for (int bf = 0; bf < NLB; ++bf)
+            *reinterpret_cast<uint4*>(sm + (which == 0 ? OFF_Q : OFF_DO) + bf * TILE_B + 5 * (128 * 16) + row * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
     tc::fence_async_smem();
     tc::fence_before_sync();
@@ -825,35 +863,30 @@ attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const
 
     if (warp == W_LOAD) {
         // ------------------------------------------------------------------ loader (fire and forget)
-        // Q / dO tiles are pre-tiled in global memory (see "operand layouts"): one 8 KB cp.async.bulk each, completion
-        // counted in bytes on bar_load -- async-proxy writes, so the MMA lane needs no proxy fence.  lse / D ride on
-        // 4-byte cp.async whose completion every lane signals with cp.async.mbarrier.arrive.noinc (32 + 1 arrivals per
-        // tile).  Padding queries are zero-filled: Q = dO = 0, lse = D = 0 give P = 1, dP = 0, dS = 0, and P^T only
-        // multiplies the zero dO rows.  The loader blocks only on a buffer being released: up to NLB - 1 tiles ahead.
-        const bf16* qsrc = Qb + (size_t)(b * H + h) * nq * 128 * D;
-        const bf16* dsrc = dOb + (size_t)(b * H + h) * nq * 128 * D;
+        const bf16* qsrc = Qb + (size_t)(b * H + h) * nq * (TILE_G / 2);
+        const bf16* dsrc = dOb + (size_t)(b * H + h) * nq * (TILE_G / 2);
         for (int t = 0; t < nq; ++t) {
             const int buf = t % NLB;
             if (t >= NLB) tc::mbar_wait(&bar_acc[1], (uint32_t)((t - NLB) & 1));   // every MMA that read this buffer has completed
-            if (lane == 0 && !((debug & 2) && t >= NLB)) {
-                tc::mbar_arrive_expect_tx(&bar_load[buf], 2 * TILE_B);
-                tc::bulk_copy_g2s(sbase + OFF_Q + buf * TILE_B, qsrc + (size_t)t * 128 * D, TILE_B, &bar_load[buf]);
-                tc::bulk_copy_g2s(sbase + OFF_DO + buf * TILE_B, dsrc + (size_t)t * 128 * D, TILE_B, &bar_load[buf]);
-            } else if (lane == 0) {
-                tc::mbar_arrive(&bar_load[buf]);
+            if (lane == 0) {
+                tc::mbar_arrive_expect_tx(&bar_load[buf], 2 * TILE_G);
+                tc::bulk_copy_g2s(sbase + OFF_Q + buf * TILE_B, qsrc + (size_t)t * (TILE_G / 2), TILE_G, &bar_load[buf]);
+                tc::bulk_copy_g2s(sbase + OFF_DO + buf * TILE_B, dsrc + (size_t)t * (TILE_G / 2), TILE_G, &bar_load[buf]);
             }
+            if (DROP) {                               // D and the row keys of the tile for the compute warps
 #pragma unroll
-            for (int it = 0; it < 4; ++it) {
-                const int r = it * 32 + lane, q = t * 128 + r;
-                const bool ok = q < S;
-                tc::cp_async4(tc::smem_u32(&lse_s[buf][r]), ok ? (const void*)(lse + stat_off + q) : (const void*)lse, ok);
-                tc::cp_async4(tc::smem_u32(&D_s[buf][r]), ok ? (const void*)(Dvec + stat_off + q) : (const void*)Dvec, ok);
-                if (DROP) rk_s[buf][r] = drop_rowkey(dc, (uint32_t)(stat_off + q));
+                for (int it = 0; it < 4; ++it) {
+                    const int r = it * 32 + lane, q = t * 128 + r;
+                    const bool ok = q < S;
+                    tc::cp_async4(tc::smem_u32(&D_s[buf][r]), ok ? (const void*)(Dvec + stat_off + q) : (const void*)Dvec, ok);
+                    rk_s[buf][r] = drop_rowkey(dc, (uint32_t)(stat_off + q));
+                }
+                tc::cp_async_mbar_arrive_noinc(&bar_load[buf]);
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&bar_load[buf]);     // releases the row-key stores
             }
-            tc::cp_async_mbar_arrive_noinc(&bar_load[buf]);
-            if (DROP) { __syncwarp(); if (lane == 0) tc::mbar_arrive(&bar_load[buf]); }   // releases the row-key stores
         }
-        tc::cp_async_wait_all();
+        if (DROP) tc::cp_async_wait_all();
     } else if (warp == W_MMA) {
         // ------------------------------------------------------------------ tensor-core issue (one lane)
         if (tc::elect_one()) {
@@ -865,50 +898,44 @@ attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const
             const tc::Desc kQ = tc::kmajor(sbase + OFF_Q, 128), kdO = tc::kmajor(sbase + OFF_DO, 128);
             const tc::Desc mQ = tc::mnmajor(sbase + OFF_Q, 128), mdO = tc::mnmajor(sbase + OFF_DO, 128);
             const tc::Desc kPT = tc::kmajor(sbase + OFF_PT, 128), kdS = tc::kmajor(sbase + OFF_DS, 128), mdS = tc::mnmajor(sbase + OFF_DS, 128);
-            auto issue_scores = [&](int n) {
+            auto issue_scores = [&](int n) {          // contraction over 48 columns: 32 + the statistics chunk + a zero chunk
                 const uint32_t off = ((n >> 1) % NLB) * TILE_B + (n & 1) * 64 * 16;
                 const uint32_t tS = tmem + (uint32_t)(n & 1) * 128u;
 #pragma unroll
-                for (int s = 0; s < D / 16; ++s)
+                for (int s = 0; s < 3; ++s)
                     tc::mma_bf16(tS, kK.adv(s * KS).u64(), kQ.adv(off + s * KS).u64(), idesc64, s > 0);
 #pragma unroll
-                for (int s = 0; s < D / 16; ++s)
+                for (int s = 0; s < 3; ++s)
                     tc::mma_bf16(tS + 64, kV.adv(s * KS).u64(), kdO.adv(off + s * KS).u64(), idesc64, s > 0);
             };
             tc::mbar_wait(&bar_load[0], 0);
+            tc::fence_after_sync();
             issue_scores(0); tc::mma_commit(&bar_S[0]);
             issue_scores(1); tc::mma_commit(&bar_S[1]);
             for (int n = 0; n < nsteps; ++n) {
                 const int i = n >> 1, hq = n & 1, s = n & 1;
                 tc::mbar_wait(&bar_cmp[s], (uint32_t)((n >> 1) & 1));           // P^T / dS^T of step n written, stage s drained
                 tc::fence_after_sync();
-                const bool ts = (debug & 512) && blockIdx.x == 0 && blockIdx.y == 0 && n < 32;
-                if (ts) g_bw2_ts[n * 8 + 0] = clock64();
                 if (n + 2 < nsteps) {
-                    if (hq == 0) { tc::mbar_wait(&bar_load[(i + 1) % NLB], (uint32_t)(((i + 1) / NLB) & 1)); if (ts) g_bw2_ts[512 + n * 4 + 0] = clock64(); }
+                    if (hq == 0) tc::mbar_wait(&bar_load[(i + 1) % NLB], (uint32_t)(((i + 1) / NLB) & 1));
                     issue_scores(n + 2);
-                    if (ts) g_bw2_ts[512 + n * 4 + 2] = clock64();
                     tc::mma_commit(&bar_S[s]);
                 }
-                if (ts) g_bw2_ts[n * 8 + 1] = clock64();
                 const uint32_t off = (i % NLB) * TILE_B + hq * 64 * 16;
-                if (!(debug & 16)) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)     // dV[key,d] += P^T[key, 64 q] dO[64 q, d]
                     tc::mma_bf16(tmem + TM_DV, kPT.adv(s * PT_B + k * KS).u64(), mdO.adv(off + k * tc::KSTEP_MN).u64(), idescKM, (n | k) != 0);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)     // dK[key,d] += dS^T[key, 64 q] Q[64 q, d]
+                for (int k = 0; k < 4; ++k)     // dK[key,d] += dS^T[key, 64 q] Q'[64 q, d]
                     tc::mma_bf16(tmem + TM_DK, kdS.adv((i & 1) * DS_B + (hq * 4 + k) * KS).u64(), mQ.adv(off + k * tc::KSTEP_MN).u64(), idescKM, (n | k) != 0);
-                }
-                if (hq == 1 && !(debug & 4)) {
-                    if (i >= 2 && !(debug & 32)) { tc::mbar_wait(&bar_dq[i & 1], (uint32_t)(((i - 2) >> 1) & 1)); tc::fence_after_sync(); }
+                if (hq == 1) {
+                    if (i >= 2) { tc::mbar_wait(&bar_dq[i & 1], (uint32_t)(((i - 2) >> 1) & 1)); tc::fence_after_sync(); }
 #pragma unroll
                     for (int k = 0; k < 8; ++k)   // dQ[q,d] = dS[q, key] K[key, d] over the 128 queries of the tile
                         tc::mma_bf16(tmem + TM_DQ + (uint32_t)(i & 1) * 32u, mdS.adv((i & 1) * DS_B + k * tc::KSTEP_MN).u64(),
                                      mK.adv(k * tc::KSTEP_MN).u64(), idescMM, k > 0);
                 }
                 tc::mma_commit(&bar_acc[s]);
-                if (ts) g_bw2_ts[n * 8 + 2] = clock64();
             }
         }
         __syncwarp();
@@ -917,17 +944,16 @@ attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const
         const int quarter = warp & 3;
         const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
         float* stg = reinterpret_cast<float*>(sm + OFF_STG + quarter * 4096);
-        for (int i = 0; i < ((debug & 32) ? 0 : nq); ++i) {
+        for (int i = 0; i < nq; ++i) {
             tc::mbar_wait(&bar_acc[1], (uint32_t)(i & 1));
             tc::fence_after_sync();
             float t[32];
-            if (!(debug & 4096)) tc::tmem_ld32(tlane + TM_DQ + (uint32_t)(i & 1) * 32u, t);
-            else { for (int c = 0; c < 32; ++c) t[c] = 0.f; }
+            tc::tmem_ld32(tlane + TM_DQ + (uint32_t)(i & 1) * 32u, t);
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) { tc::mbar_arrive(&bar_dq[i & 1]); tc::bulk_wait_read0(); }   // staging block free again
             __syncwarp();
-            if (!(debug & 2048)) {
+            {
                 // Row `lane` is 128 contiguous bytes (the bulk reduce needs the block linear), so a straight float4 store
                 // would put all lanes of a quarter-warp on the same four banks (8-way conflict, ~1000 smem cycles per
                 // tile that also stall the tensor core's operand reads).  Lane l instead writes its chunks in the order
@@ -949,12 +975,12 @@ attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const
                 for (int j = 0; j < 8; ++j)
                     *reinterpret_cast<float4*>(stg + lane * 32 + ((j + rot) & 7) * 4) = v[j];
             }
-            if (!(debug & 1024)) tc::fence_async_smem();
+            tc::fence_async_smem();
             __syncwarp();
             if (lane == 0) {
                 const int q0 = i * 128 + quarter * 32;
                 const int rows = min(32, S - q0);
-                if (rows > 0 && !(debug & 1)) tc::bulk_reduce_add_f32(dQacc + head_off + (size_t)q0 * D, stg, (uint32_t)rows * (D * 4));
+                if (rows > 0) tc::bulk_reduce_add_f32(dQacc + head_off + (size_t)q0 * D, stg, (uint32_t)rows * (D * 4));
                 tc::bulk_commit();
             }
         }
@@ -968,56 +994,37 @@ attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const
         const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
         const int c0 = cg * CPT;
         const uint32_t kterm = (uint32_t)key * 0x85EBCA6Bu;
+        uint8_t* const pt0 = sm + OFF_PT + (cg * (CPT / 8)) * (128 * 16) + row * 16;
+        uint8_t* const ds0 = sm + OFF_DS + (cg * (CPT / 8)) * (128 * 16) + row * 16;
         for (int n = 0; n < nsteps; ++n) {
-            const int i = n >> 1, hq = n & 1, s = n & 1, buf = i % NLB;
-            if (hq == 0) tc::mbar_wait(&bar_load[buf], (uint32_t)((i / NLB) & 1));  // lse / D / row keys of the tile
-            const bool ts = (debug & 512) && blockIdx.x == 0 && blockIdx.y == 0 && n < 32 && warp == 5 && lane == 0;
-            if (ts) g_bw2_ts[n * 8 + 3] = clock64();
+            const int i = n >> 1, hq = n & 1, s = n & 1;
+            if (DROP && hq == 0) tc::mbar_wait(&bar_load[i % NLB], (uint32_t)((i / NLB) & 1));   // D / row keys of the tile
             tc::mbar_wait(&bar_S[s], (uint32_t)((n >> 1) & 1));
             tc::fence_after_sync();
-            if (ts) g_bw2_ts[n * 8 + 4] = clock64();
-            float st[CPT], dp[CPT];
-            {
-                uint32_t r0[CPT], r1[CPT];
-                if constexpr (CPT == 16) {
-                    tc::tmem_ld16_nowait(tlane + (uint32_t)s * 128u + c0, r0);
-                    tc::tmem_ld16_nowait(tlane + (uint32_t)s * 128u + 64u + c0, r1);
-                } else {
-                    tc::tmem_ld32_nowait(tlane + (uint32_t)s * 128u + c0, r0);
-                    tc::tmem_ld32_nowait(tlane + (uint32_t)s * 128u + 64u + c0, r1);
-                }
-                tc::tmem_wait_ld();
-#pragma unroll
-                for (int c = 0; c < CPT; ++c) { st[c] = __uint_as_float(r0[c]); dp[c] = __uint_as_float(r1[c]); }
+            uint32_t r0[CPT], r1[CPT];
+            if constexpr (CPT == 16) {
+                tc::tmem_ld16_nowait(tlane + (uint32_t)s * 128u + c0, r0);
+                tc::tmem_ld16_nowait(tlane + (uint32_t)s * 128u + 64u + c0, r1);
+            } else {
+                tc::tmem_ld32_nowait(tlane + (uint32_t)s * 128u + c0, r0);
+                tc::tmem_ld32_nowait(tlane + (uint32_t)s * 128u + 64u + c0, r1);
             }
-            if (ts) g_bw2_ts[n * 8 + 5] = clock64();
-            if (!valid_k) {                           // padding keys: exp2(-inf) = 0 -> P = dS = 0
-#pragma unroll
-                for (int c = 0; c < CPT; ++c) st[c] = -INFINITY;
-            }
-            if (!(debug & 8)) {
-            const float* ls_p = &lse_s[buf][hq * 64 + c0];
-            const float* dd_p = &D_s[buf][hq * 64 + c0];
-            const uint32_t* rk_p = &rk_s[buf][hq * 64 + c0];
+            tc::tmem_wait_ld();
             uint4 pk[CPT / 8], dk[CPT / 8];
 #pragma unroll
             for (int c8 = 0; c8 < CPT / 8; ++c8) {
-                const float4 l0 = *reinterpret_cast<const float4*>(ls_p + c8 * 8);
-                const float4 l1 = *reinterpret_cast<const float4*>(ls_p + c8 * 8 + 4);
-                const float4 d0 = *reinterpret_cast<const float4*>(dd_p + c8 * 8);
-                const float4 d1 = *reinterpret_cast<const float4*>(dd_p + c8 * 8 + 4);
-                const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-                const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
                 float p[8], ds[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    p[c] = ex2_approx(fmaf(st[c8 * 8 + c], scale_log2, -ls[c]));
+                    const int cc = c8 * 8 + c;
+                    p[c] = valid_k ? ex2_approx(__uint_as_float(r0[cc])) : 0.f;      // padding keys: P = dS = 0
                     if (DROP) {
-                        const float mk = (lowbias32(rk_p[c8 * 8 + c] ^ kterm) >= dc.thresh) ? dc.inv_keep : 0.f;
-                        ds[c] = p[c] * fmaf(dp[c8 * 8 + c], mk, -dd[c]);
+                        const int qi = hq * 64 + c0 + cc;
+                        const float mk = (lowbias32(rk_s[i % NLB][qi] ^ kterm) >= dc.thresh) ? dc.inv_keep : 0.f;
+                        ds[c] = p[c] * fmaf(__uint_as_float(r1[cc]), mk, -D_s[i % NLB][qi]);
                         p[c] *= mk;                                       // P^T feeds dV with the dropped probabilities
                     } else {
-                        ds[c] = p[c] * (dp[c8 * 8 + c] - dd[c]);          // unscaled; `scale` is applied to dQ / dK at the end
+                        ds[c] = p[c] * __uint_as_float(r1[cc]);           // unscaled; `scale` is applied to dQ / dK at the end
                     }
                 }
                 pk[c8].x = tc::pack_bf16(p[0], p[1]); pk[c8].y = tc::pack_bf16(p[2], p[3]);
@@ -1026,20 +1033,17 @@ attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const
                 dk[c8].z = tc::pack_bf16(ds[4], ds[5]); dk[c8].w = tc::pack_bf16(ds[6], ds[7]);
             }
             if (n >= 2) tc::mbar_wait(&bar_acc[s], (uint32_t)(((n >> 1) - 1) & 1));   // dV / dK of step n-2 have read P^T[s]
-            uint8_t* pt = sm + OFF_PT + s * PT_B + (cg * (CPT / 8)) * (128 * 16) + row * 16;
-            uint8_t* dst = sm + OFF_DS + (i & 1) * DS_B + (hq * 8 + cg * (CPT / 8)) * (128 * 16) + row * 16;
+            uint8_t* pt = pt0 + s * PT_B;
+            uint8_t* dst = ds0 + (i & 1) * DS_B + hq * 8 * (128 * 16);
 #pragma unroll
             for (int c8 = 0; c8 < CPT / 8; ++c8) {
                 *reinterpret_cast<uint4*>(pt + c8 * (128 * 16)) = pk[c8];
                 *reinterpret_cast<uint4*>(dst + c8 * (128 * 16)) = dk[c8];
             }
-            }
-            if (ts) g_bw2_ts[n * 8 + 6] = clock64();
-            if (!(debug & 64)) tc::fence_async_smem();
+            tc::fence_async_smem();
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&bar_cmp[s]);
-            if (ts) g_bw2_ts[n * 8 + 7] = clock64();
         }
         // ---- epilogue: dK (scaled), dV of this key tile ----
         tc::mbar_wait(&bar_acc[1], (uint32_t)(((nsteps - 1) >> 1) & 1));
@@ -1049,8 +1053,8 @@ attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const
             tc::tmem_ld8(tlane + TM_DK + cg * 8, t);
             if (valid_k) {
                 float* dkp = dKh + head_off + (size_t)key * D + cg * 8;
-                *reinterpret_cast<float4*>(dkp) = make_float4(t[0] * scale, t[1] * scale, t[2] * scale, t[3] * scale);
-                *reinterpret_cast<float4*>(dkp + 4) = make_float4(t[4] * scale, t[5] * scale, t[6] * scale, t[7] * scale);
+                *reinterpret_cast<float4*>(dkp) = make_float4(t[0] * scale_dk, t[1] * scale_dk, t[2] * scale_dk, t[3] * scale_dk);
+                *reinterpret_cast<float4*>(dkp + 4) = make_float4(t[4] * scale_dk, t[5] * scale_dk, t[6] * scale_dk, t[7] * scale_dk);
             }
             tc::tmem_ld8(tlane + TM_DV + cg * 8, t);
             if (valid_k) {
@@ -1065,7 +1069,7 @@ attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const
                 float* dkp = dKh + head_off + (size_t)key * D + cg * 16;
 #pragma unroll
                 for (int c = 0; c < 16; c += 4)
-                    *reinterpret_cast<float4*>(dkp + c) = make_float4(t[c] * scale, t[c + 1] * scale, t[c + 2] * scale, t[c + 3] * scale);
+                    *reinterpret_cast<float4*>(dkp + c) = make_float4(t[c] * scale_dk, t[c + 1] * scale_dk, t[c + 2] * scale_dk, t[c + 3] * scale_dk);
             }
             tc::tmem_ld16(tlane + TM_DV + cg * 16, t);
             if (valid_k) {
@@ -1086,12 +1090,12 @@ struct AttnWs {
     float *Dvec, *dQacc, *dKh, *dVh;
 };
 static size_t attn_ws_bytes(int64_t B, int64_t S, int H, int Hkv, int d) {
-    const size_t qe = (size_t)B * H * S * d, ke = (size_t)B * Hkv * S * d, qp = (size_t)B * H * pad128(S) * d;
+    const size_t qe = (size_t)B * H * S * d, ke = (size_t)B * Hkv * S * d, qp = (size_t)B * H * pad128(S) * (d + 8);
     return align_up(qp * 2) * 2 + align_up(ke * 2) * 2 + align_up((size_t)B * H * S * 4) + 3 * align_up(qe * 4) + 1024;
 }
 static bool attn_carve(AttnWs& w, void* ws, size_t bytes, int64_t B, int64_t S, int H, int Hkv, int d) {
     Arena ar(ws, bytes);
-    const size_t qe = (size_t)B * H * S * d, ke = (size_t)B * Hkv * S * d, qp = (size_t)B * H * pad128(S) * d;
+    const size_t qe = (size_t)B * H * S * d, ke = (size_t)B * Hkv * S * d, qp = (size_t)B * H * pad128(S) * (d + 8);
     w.Qb = ar.take<bf16>(qp); w.Kb = ar.take<bf16>(ke); w.Vb = ar.take<bf16>(ke); w.dOb = ar.take<bf16>(qp);
     w.Dvec = ar.take<float>((size_t)B * H * S);
     w.dQacc = ar.take<float>(qe); w.dKh = ar.take<float>(qe); w.dVh = ar.take<float>(qe);
@@ -1107,11 +1111,11 @@ static inline unsigned nb256(int64_t n) { return (unsigned)((n + 255) / 256); }
 
 static int attn_prep_all(const float* q, const float* k, const float* v, const AttnWs& w, int64_t B, int64_t S,
                          int H, int Hkv, int d, const float* freqs, cudaStream_t st) {
-    attn_prep_kernel<<<nb256(B * pad128(S) * H * (d / 8)), 256, 0, st>>>(q, w.Qb, B, S, H, d, freqs, 1);
+    attn_prep_kernel<<<nb256(B * pad128(S) * H * (d / 8)), 256, 0, st>>>(q, w.Qb, B, S, H, d, freqs, 1, (1.0f / sqrtf((float)d)) * 1.4426950408889634f);
     GAOT_LAUNCH_CHECK();
-    attn_prep_kernel<<<nb256(B * S * Hkv * (d / 8)), 256, 0, st>>>(k, w.Kb, B, S, Hkv, d, freqs, 0);
+    attn_prep_kernel<<<nb256(B * S * Hkv * (d / 8)), 256, 0, st>>>(k, w.Kb, B, S, Hkv, d, freqs, 0, 1.0f);
     GAOT_LAUNCH_CHECK();
-    attn_prep_kernel<<<nb256(B * S * Hkv * (d / 8)), 256, 0, st>>>(v, w.Vb, B, S, Hkv, d, nullptr, 0);
+    attn_prep_kernel<<<nb256(B * S * Hkv * (d / 8)), 256, 0, st>>>(v, w.Vb, B, S, Hkv, d, nullptr, 0, 1.0f);
     GAOT_LAUNCH_CHECK();
     return GAOT_OK;
 }
@@ -1121,10 +1125,6 @@ static int attn_prep_all(const float* q, const float* k, const float* v, const A
 using namespace gaot;
 
 extern "C" {
-
-int gaot_debug_bw2_timestamps(long long* host, int n) {
-    return cudaMemcpyFromSymbol(host, g_bw2_ts, sizeof(long long) * (size_t)(n < 1024 ? n : 1024)) == cudaSuccess ? 0 : 1;
-}
 
 size_t gaot_attn_workspace_bytes(int64_t B, int64_t S, int32_t H, int32_t Hkv, int32_t d) {
     return attn_ws_bytes(B, S, H, Hkv, d);
@@ -1143,7 +1143,7 @@ static int attn_launch_fwd(const AttnWs& w, int64_t B, int64_t S, int H, int Hkv
                            void* out, int out_bf16, float* out32, float* lse, cudaStream_t st) {
     GAOT_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "attn: dropout_p must be in [0,1)");
     GAOT_CHECK_ARG((int64_t)B * H * S < ((int64_t)1 << 32), "attn: B*H*S too large for the dropout counter");
-    const float scale_log2 = (1.0f / sqrtf((float)d)) * 1.4426950408889634f;
+    const float scale_log2 = 1.0f;                   // Q is stored pre-multiplied by (1/sqrt(d)) log2(e): see "operand layouts"
     const DropCfg dc = make_drop(dropout_p, seed);
     const bool drop = dropout_p > 0.f;
     const char* dbg_env = getenv("GAOT_ATTN_DEBUG");
@@ -1182,7 +1182,8 @@ int gaot_attn_forward(const float* q, const float* k, const float* v, int64_t B,
 static int attn_launch_bwd(const AttnWs& w, const float* lse, int64_t B, int64_t S, int H, int Hkv, int d,
                            float dropout_p, uint64_t seed, cudaStream_t st) {
     GAOT_CUDA(cudaMemsetAsync(w.dQacc, 0, (size_t)B * H * S * d * sizeof(float), st));
-    const float scale = 1.0f / sqrtf((float)d), scale_log2 = scale * 1.4426950408889634f;
+    // Q is stored pre-multiplied by scale * log2(e): dK = scale dS^T Q = ln(2) dS^T Q'
+    const float scale = 1.0f / sqrtf((float)d), scale_dk = 0.6931471805599453f;
     const char* dbg_env = getenv("GAOT_ATTN_DEBUG");
     const int dbg = dbg_env ? atoi(dbg_env) : 0;
     dim3 grid((unsigned)((S + 127) / 128), (unsigned)H, (unsigned)B);
@@ -1193,8 +1194,8 @@ static int attn_launch_bwd(const AttnWs& w, const float* lse, int64_t B, int64_t
         const int ncw = (dbg & 256) ? 8 : 16;
 #define GAOT_BWD2_LAUNCH(NCW, DR)                                                                                      \
     do { GAOT_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<NCW, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bw2::SMEM)); \
-         attn_bwd2_kernel<NCW, DR><<<grid, (NCW + 6) * 32, bw2::SMEM, st>>>(w.Qb, w.Kb, w.Vb, w.dOb, lse, w.Dvec, w.dQacc, w.dKh, w.dVh, \
-                                                                           (int)S, H, Hkv, scale, scale_log2, dbg, dc); } while (0)
+         attn_bwd2_kernel<NCW, DR><<<grid, (NCW + 6) * 32, bw2::SMEM, st>>>(w.Qb, w.Kb, w.Vb, w.dOb, w.Dvec, w.dQacc, w.dKh, w.dVh, \
+                                                                           (int)S, H, Hkv, scale, scale_dk, dc); } while (0)
         if (ncw == 16) { if (drop) GAOT_BWD2_LAUNCH(16, true); else GAOT_BWD2_LAUNCH(16, false); }
         else           { if (drop) GAOT_BWD2_LAUNCH(8, true);  else GAOT_BWD2_LAUNCH(8, false); }
 #undef GAOT_BWD2_LAUNCH
@@ -1204,7 +1205,7 @@ static int attn_launch_bwd(const AttnWs& w, const float* lse, int64_t B, int64_t
 #define GAOT_BWD_LAUNCH(DD, DR, SM)                                                                                   \
     do { GAOT_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<DD, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM))); \
          attn_bwd_kernel<DD, DR><<<grid, 256, (SM), st>>>(w.Qb, w.Kb, w.Vb, w.dOb, lse, w.Dvec, w.dQacc, w.dKh, w.dVh,    \
-                                                         (int)S, H, Hkv, scale, scale_log2, dbg, dc); } while (0)
+                                                         (int)S, H, Hkv, scale, scale_dk, 1.0f, dbg, dc); } while (0)
     if (d == 32) {
         const size_t smem = 6 * 128 * 32 * 2 + 128 * 64 * 2 + 128 * 128 * 2;
         if (drop) GAOT_BWD_LAUNCH(32, true, smem); else GAOT_BWD_LAUNCH(32, false, smem);
@@ -1228,7 +1229,7 @@ int gaot_attn_backward(const float* q, const float* k, const float* v, const flo
     if (!attn_carve(w, ws, ws_bytes, B, S, H, Hkv, d)) { set_error("attn_backward: workspace too small"); return GAOT_ERR_WORKSPACE; }
     rc = attn_prep_all(q, k, v, w, B, S, H, Hkv, d, rope_freqs, st);
     if (rc) return rc;
-    attn_bwd_prep_kernel<<<nb256(B * pad128(S) * H), 256, 0, st>>>(d_out, out, w.dOb, w.Dvec, B, S, H, d);
+    attn_bwd_prep_kernel<<<nb256(B * pad128(S) * H), 256, 0, st>>>(d_out, out, w.dOb, w.Dvec, w.Qb, lse, dropout_p > 0.f ? 0 : 1, B, S, H, d);
     GAOT_LAUNCH_CHECK();
     rc = attn_launch_bwd(w, lse, B, S, H, Hkv, d, dropout_p, seed, st);
     if (rc) return rc;
@@ -1243,12 +1244,12 @@ int gaot_attn_backward(const float* q, const float* k, const float* v, const flo
 
 // ---- fused-block flavour: operands stay in the kernels' own bf16 per-head layout between forward and backward ----
 size_t gaot_attn_packed_bytes(int64_t B, int64_t S, int32_t H, int32_t Hkv, int32_t d) {
-    return align_up((size_t)B * H * pad128(S) * d * 2) + 2 * align_up((size_t)B * Hkv * S * d * 2);
+    return align_up((size_t)B * H * pad128(S) * (d + 8) * 2) + 2 * align_up((size_t)B * Hkv * S * d * 2);
 }
 
 static void attn_packed_ptrs(AttnWs& w, void* packed, int64_t B, int64_t S, int H, int Hkv, int d) {
     char* p = (char*)packed;
-    w.Qb = (bf16*)p; p += align_up((size_t)B * H * pad128(S) * d * 2);
+    w.Qb = (bf16*)p; p += align_up((size_t)B * H * pad128(S) * (d + 8) * 2);
     w.Kb = (bf16*)p; p += align_up((size_t)B * Hkv * S * d * 2);
     w.Vb = (bf16*)p;
 }
@@ -1262,13 +1263,13 @@ int gaot_attn_fused_forward(const void* qkv, int64_t ld, int64_t B, int64_t S, i
     GAOT_CHECK_ARG(qkv && packed && out && out_f32 && lse && ld % 8 == 0, "attn_fused_forward: bad pointer / ld");
     AttnWs w{};
     attn_packed_ptrs(w, packed, B, S, H, Hkv, d);
-    attn_pack_qkv_kernel<<<nb256(B * pad128(S) * (H + 2 * Hkv) * (d / 8)), 256, 0, st>>>((const bf16*)qkv, ld, w.Qb, w.Kb, w.Vb, B, S, H, Hkv, d, rope_freqs);
+    attn_pack_qkv_kernel<<<nb256(B * pad128(S) * (H + 2 * Hkv) * (d / 8)), 256, 0, st>>>((const bf16*)qkv, ld, w.Qb, w.Kb, w.Vb, B, S, H, Hkv, d, rope_freqs, (1.0f / sqrtf((float)d)) * 1.4426950408889634f);
     GAOT_LAUNCH_CHECK();
     return attn_launch_fwd(w, B, S, H, Hkv, d, dropout_p, seed, out, 1, out_f32, lse, st);
 }
 
 size_t gaot_attn_fused_backward_workspace_bytes(int64_t B, int64_t S, int32_t H, int32_t d) {
-    const size_t qe = (size_t)B * H * S * d, qp = (size_t)B * H * pad128(S) * d;
+    const size_t qe = (size_t)B * H * S * d, qp = (size_t)B * H * pad128(S) * (d + 8);
     return align_up(qp * 2) + align_up((size_t)B * H * S * 4) + 3 * align_up(qe * 4) + 1024;
 }
 
@@ -1283,11 +1284,11 @@ int gaot_attn_fused_backward(const void* packed, const float* out, const void* d
     AttnWs w{};
     attn_packed_ptrs(w, const_cast<void*>(packed), B, S, H, Hkv, d);
     Arena ar(ws, ws_bytes);
-    const size_t qe = (size_t)B * H * S * d, qp = (size_t)B * H * pad128(S) * d;
+    const size_t qe = (size_t)B * H * S * d, qp = (size_t)B * H * pad128(S) * (d + 8);
     w.dOb = ar.take<bf16>(qp); w.Dvec = ar.take<float>((size_t)B * H * S);
     w.dQacc = ar.take<float>(qe); w.dKh = ar.take<float>(qe); w.dVh = ar.take<float>(qe);
     if (!ar.ok()) { set_error("attn_fused_backward: workspace too small"); return GAOT_ERR_WORKSPACE; }
-    attn_bwd_prep_bf16_kernel<<<nb256(B * pad128(S) * H), 256, 0, st>>>((const bf16*)d_out, out, w.dOb, w.Dvec, B, S, H, d);
+    attn_bwd_prep_bf16_kernel<<<nb256(B * pad128(S) * H), 256, 0, st>>>((const bf16*)d_out, out, w.dOb, w.Dvec, w.Qb, lse, dropout_p > 0.f ? 0 : 1, B, S, H, d);
     GAOT_LAUNCH_CHECK();
     rc = attn_launch_bwd(w, lse, B, S, H, Hkv, d, dropout_p, seed, st);
     if (rc) return rc;

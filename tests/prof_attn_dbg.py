@@ -29,15 +29,3 @@ for dbg in sys.argv[1:]:
         lib.gaot_profile_enable(0)
     out = {l.split()[0]: float(l.split()[2]) / int(l.split()[1]) for l in buf.value.decode().splitlines()}
     print(f"debug={dbg:>4}: " + "  ".join(f"{n} {t:.3f} ms" for n, t in out.items()), flush=True)
-if os.environ.get("BW2_TS"):
-    import numpy as np
-    os.environ["GAOT_ATTN_DEBUG"] = os.environ["BW2_TS"]
-    o = ops.attention(q, k, v, H, H, rope_freqs=fr); o.backward(go); torch.cuda.synchronize()
-    arr = (ctypes.c_longlong * 1024)()
-    lib.gaot_debug_bw2_timestamps.argtypes = [ctypes.c_void_p, ctypes.c_int]
-    lib.gaot_debug_bw2_timestamps(arr, 1024)
-    a = np.array(arr[:256]).reshape(32, 8); x = np.array(arr[512:640]).reshape(32, 4)
-    t0 = a[0, 3]
-    print("step: mma[cmp_ready scores_committed acc_committed] | cmp5[before_S_wait S_ready ld_done math_done arrived]  (clk rel.)")
-    for n in range(24):
-        print(n, (a[n, :3] - t0).tolist(), "|", (a[n, 3:] - t0).tolist(), "| mma[load_ok fence_done issued]", (x[n, :3] - t0).tolist())
