@@ -118,7 +118,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="drivaernet500k", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gno-precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--gno-precision", default="bf16", choices=["fp32", "bf16"],
+                    help="per-edge kernel MLP operands: bf16 tcgen05 (rtol 2e-2 tier of the north star, default) or fp32 CUDA cores (rtol 1e-5 tier)")
     ap.add_argument("--shard", action="store_true", help="intra-sample sharding: all ranks cooperate on ONE sample (strong scaling)")
     ap.add_argument("--profile-step", action="store_true", help="warm up, then run ONE step between cudaProfilerStart/Stop (for ncu --profile-from-start off) and exit")
     args = ap.parse_args()
@@ -263,7 +264,7 @@ def main():
         calls, ms, work = int(calls), float(ms), float(work)
         kernels[name] = {"calls_per_step": calls / args.steps, "ms_per_step": ms / args.steps, "share_of_step": ms / ms_total,
                          "avg_launch_ms": ms / calls, "work_per_launch": work / calls}
-    tensor_bound = {"attn_fwd", "attn_bwd"}
+    tensor_bound = {"attn_fwd", "attn_bwd", "linear_fwd", "linear_bwd_x", "linear_bwd_w"}
     for name, kd in kernels.items():
         rate = kd["work_per_launch"] / (kd["avg_launch_ms"] * 1e-3)
         if name in tensor_bound:
@@ -274,7 +275,12 @@ def main():
     roofline = None
     if dom:
         kd = kernels[dom]
-        traffic = {"attn_bwd": None, "attn_fwd": None}.get(dom)
+        # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/traffic.json,
+        # written by profiles/summarize.py from dram__bytes_read.sum + dram__bytes_write.sum); null if never captured
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(dom)
         roofline = {"kernel": dom, "bound": kd["bound"], "achieved": kd["achieved"], "peak": kd["peak"], "unit": kd["unit"],
                     "frac": kd["frac"], "traffic": traffic, "peak_source": f"{pk['src']} (MEASURED_PEAKS.json, sustained bf16 / copy bandwidth)",
                     "share_of_step": kd["share_of_step"]}
@@ -287,7 +293,9 @@ def main():
                "note": "encoder and decoder launches averaged (same E for knn k=1)", "precision": args.gno_precision}
     out = {"metric": "fwd+bwd samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if args.shard else "weak", "vs_baseline": None,
-           "dtype": "f32 (GNO, dense layers) + bf16 tensor-core operands / f32 accumulate (attention)", "data": "synthetic",
+           "dtype": ("bf16 tensor-core operands / f32 accumulate (attention, transformer dense layers" +
+                     (", GNO edge MLP)" if args.gno_precision == "bf16" else "); f32 GNO edge MLP") +
+                     "; f32 residual stream, statistics, node MLPs, optimizer"), "data": "synthetic",
            "config": config, "clocks": clk,
            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                    "ms_per_step": ms_e2e / args.steps},

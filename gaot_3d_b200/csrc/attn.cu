@@ -315,7 +315,7 @@ template <int D, bool DROP>
 __global__ void __launch_bounds__(128, 2)
 attn_fwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const bf16* __restrict__ Vb,
                 void* __restrict__ out_v, int out_bf16, float* __restrict__ out32, float* __restrict__ lse, int S, int H, int Hkv,
-                float scale_log2, int debug, const DropCfg dc) {
+                const DropCfg dc) {
     extern __shared__ __align__(1024) uint8_t sm[];
     __shared__ uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
@@ -441,12 +441,10 @@ attn_fwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
             for (int c = 0; c < 128; ++c) if (c >= kvalid) sv[c] = -INFINITY;
         }
         float mr = fmax3(sv[0], sv[1], sv[2]);
-        if (!(debug & 64)) {
 #pragma unroll
         for (int c = 3; c + 1 < 128; c += 2) mr = fmax3(mr, sv[c], sv[c + 1]);
         mr = fmaxf(mr, sv[127]);
-        }
-        const float mx = fmaxf(m, mr * scale_log2);
+        const float mx = fmaxf(m, mr);
         alpha_prev = ex2_approx(m - mx);                // m = -inf on the first tile -> 0
         const float nmx = -mx;
         float rs = 0.f;
@@ -455,8 +453,7 @@ attn_fwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
             float p[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                p[c] = fmaf(sv[c8 * 8 + c], scale_log2, nmx);
-                if (!(debug & 32)) p[c] = ex2_approx(p[c]);
+                p[c] = ex2_approx(sv[c8 * 8 + c] + nmx);       // Q is pre-scaled: the scores are already in the log2 domain
                 if (DROP) {
                     rs += p[c];
                     p[c] = drop_keep(dc, rowkey, (uint32_t)(j * 128 + c8 * 8 + c)) ? p[c] * dc.inv_keep : 0.f;
@@ -533,7 +530,7 @@ __global__ void __launch_bounds__(256, 2)
 attn_bwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const bf16* __restrict__ Vb,
                 const bf16* __restrict__ dOb, const float* __restrict__ lse, const float* __restrict__ Dvec,
                 float* __restrict__ dQacc, float* __restrict__ dKh, float* __restrict__ dVh,
-                int S, int H, int Hkv, float scale, float scale_dk, float scale_log2, int debug, const DropCfg dc) {
+                int S, int H, int Hkv, float scale, float scale_dk, const DropCfg dc) {
     extern __shared__ __align__(1024) uint8_t sm[];
     __shared__ uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
@@ -625,7 +622,7 @@ attn_bwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
             const int qq = q0 + row;
             float t[32];
             tc::tmem_ld32(tlane + TM_DQ + half * 32, t);
-            if (qq < S && !(debug & 1)) {
+            if (qq < S) {
 #pragma unroll
                 for (int c = 0; c < 32; c += 4)
                     atomicAdd(reinterpret_cast<float4*>(dQacc + head_off + (size_t)qq * D + half * 32 + c),
@@ -639,7 +636,7 @@ attn_bwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
         for (int c = 0; c < 16; c += 4)
             *reinterpret_cast<float4*>(xaddr(lane, c)) = make_float4(t[c] * scale, t[c + 1] * scale, t[c + 2] * scale, t[c + 3] * scale);
         __syncwarp();
-        if (!(debug & 1)) {
+        {
 #pragma unroll
             for (int it = 0; it < 4; ++it) {          // 8 rows x 64 B per warp instruction
                 const int r = it * 8 + (lane >> 2), ch = lane & 3;
@@ -664,8 +661,8 @@ attn_bwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
         for (int hq = 0; hq < 2; ++hq) {
             tc::mbar_wait(&mbar, ph); ph ^= 1;        // scores of (i, hq) ready; every earlier MMA has completed
             tc::fence_after_sync();
-            if (hq == 0 && i > 0 && !(debug & 8)) dq_epilogue((i - 1) * 128);
-            if (!(debug & 16)) {
+            if (hq == 0 && i > 0) dq_epilogue((i - 1) * 128);
+            {
                 const int c0 = half * 32;             // this thread's 32 query columns of the half
                 float st[32], dp[32];
                 {
@@ -695,8 +692,7 @@ attn_bwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
                     float p[8], ds[8];
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        p[c] = fmaf(st[c8 * 8 + c], scale_log2, nl[c]);
-                        if (!(debug & 2)) p[c] = ex2_approx(p[c]);
+                        p[c] = ex2_approx(st[c8 * 8 + c] + nl[c]);   // Q is pre-scaled: scores already in the log2 domain
                         if (DROP) {
                             const float mk = (lowbias32(rk_p[c8 * 8 + c] ^ kterm) >= dc.thresh) ? dc.inv_keep : 0.f;
                             ds[c] = p[c] * fmaf(dp[c8 * 8 + c], mk, -dd[c]);
@@ -740,7 +736,7 @@ attn_bwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
                     for (int s = 0; s < 4; ++s)   // dK[key,d] += dS^T[key, 64 q] Q[64 q, d]
                         tc::mma_bf16(tmem + TM_DK, kdS.adv((hq * 4 + s) * KS).u64(), mQ.adv(off + s * tc::KSTEP_MN).u64(), idescKM,
                                      (i > 0) || (hq > 0) || (s > 0));
-                    if (hq == 1 && !(debug & 4)) {
+                    if (hq == 1) {
 #pragma unroll
                         for (int s = 0; s < 8; ++s)   // dQ[q,d] = dS[q, key] K[key, d] over all 128 queries of the tile
                             tc::mma_bf16(tmem + TM_DQ, mdS.adv(s * tc::KSTEP_MN).u64(), mK.adv(s * tc::KSTEP_MN).u64(), idescMM, s > 0);
@@ -1143,16 +1139,13 @@ static int attn_launch_fwd(const AttnWs& w, int64_t B, int64_t S, int H, int Hkv
                            void* out, int out_bf16, float* out32, float* lse, cudaStream_t st) {
     GAOT_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "attn: dropout_p must be in [0,1)");
     GAOT_CHECK_ARG((int64_t)B * H * S < ((int64_t)1 << 32), "attn: B*H*S too large for the dropout counter");
-    const float scale_log2 = 1.0f;                   // Q is stored pre-multiplied by (1/sqrt(d)) log2(e): see "operand layouts"
     const DropCfg dc = make_drop(dropout_p, seed);
     const bool drop = dropout_p > 0.f;
-    const char* dbg_env = getenv("GAOT_ATTN_DEBUG");
-    const int dbg = dbg_env ? atoi(dbg_env) : 0;
     dim3 grid((unsigned)((S + 127) / 128), (unsigned)H, (unsigned)B);
     GAOT_TIME_KERNEL("attn_fwd", st, 4.0 * (double)B * H * (double)S * (double)S * d);
 #define GAOT_FWD_LAUNCH(DD, DR, SM)                                                                                   \
     do { GAOT_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DD, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM))); \
-         attn_fwd_kernel<DD, DR><<<grid, 128, (SM), st>>>(w.Qb, w.Kb, w.Vb, out, out_bf16, out32, lse, (int)S, H, Hkv, scale_log2, dbg, dc); } while (0)
+         attn_fwd_kernel<DD, DR><<<grid, 128, (SM), st>>>(w.Qb, w.Kb, w.Vb, out, out_bf16, out32, lse, (int)S, H, Hkv, dc); } while (0)
     if (d == 32) {
         const size_t smem = 3 * 128 * 32 * 2 + 2 * 128 * 48 * 2 + 128 * 128 * 2;
         if (drop) GAOT_FWD_LAUNCH(32, true, smem); else GAOT_FWD_LAUNCH(32, false, smem);
@@ -1205,7 +1198,7 @@ static int attn_launch_bwd(const AttnWs& w, const float* lse, int64_t B, int64_t
 #define GAOT_BWD_LAUNCH(DD, DR, SM)                                                                                   \
     do { GAOT_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<DD, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM))); \
          attn_bwd_kernel<DD, DR><<<grid, 256, (SM), st>>>(w.Qb, w.Kb, w.Vb, w.dOb, lse, w.Dvec, w.dQacc, w.dKh, w.dVh,    \
-                                                         (int)S, H, Hkv, scale, scale_dk, 1.0f, dbg, dc); } while (0)
+                                                         (int)S, H, Hkv, scale, scale_dk, dc); } while (0)
     if (d == 32) {
         const size_t smem = 6 * 128 * 32 * 2 + 128 * 64 * 2 + 128 * 128 * 2;
         if (drop) GAOT_BWD_LAUNCH(32, true, smem); else GAOT_BWD_LAUNCH(32, false, smem);

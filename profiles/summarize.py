@@ -49,4 +49,25 @@ for rep in sorted(glob.glob(os.path.join(src, "prof_*.ncu-rep"))):
         for i, h in enumerate(hdr):
             if h in KEYS or h in ("Kernel Name",):
                 f.write(f"{h} = {vals[i]} {units[i]}\n")
+# DRAM traffic per launch of each captured kernel -> profiles/traffic.json (read by bench.py's roofline.traffic)
+import json
+alias = {"attn_bwd2_kernel": "attn_bwd", "attn_bwd_kernel": "attn_bwd", "attn_fwd_kernel": "attn_fwd", "attn_fwd2_kernel": "attn_fwd",
+         "gno_fwd_tc_kernel": "gno_fwd", "gno_bwd_tc_kernel": "gno_bwd", "gemm_tc_kernel": "linear_fwd", "knn_kernel": "knn_search"}
+tp = "profiles/traffic.json"
+traffic = json.load(open(tp)) if os.path.exists(tp) else {}
+for rep in sorted(glob.glob(os.path.join(src, "prof_*.ncu-rep"))):
+    name = os.path.basename(rep)[5:-8]
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    if len(rows) < 3:
+        continue
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    tot = 0.0
+    for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        if key in hdr:
+            i = hdr.index(key)
+            tot += float(vals[i].replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[i], 1)
+    if name in alias:
+        traffic[alias[name]] = tot
+json.dump(traffic, open(tp, "w"), indent=1, sort_keys=True)
 print(os.listdir("profiles"))
