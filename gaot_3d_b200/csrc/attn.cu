@@ -25,15 +25,16 @@ namespace gaot {
 using bf16 = __nv_bfloat16;
 
 // --------------------------------------------------------------------------- operand layouts
-// K and V stay row-major bf16 [B,Hkv,S,d].  Q and dO are stored PRE-TILED: per (b,h) ceil(S/128) tiles of 128 rows, each
+// Q, K, V and dO are all stored PRE-TILED in bf16: per (b,h) ceil(S/128) tiles of 128 rows, each
 // tile already in the kernels' chunk-major shared-memory layout (tc05.cuh: 16-byte chunk c of row r at c*128*16 + r*16),
 // rows >= S zero.  A tile is one contiguous block that the backward's loader moves with a single cp.async.bulk (TMA
 // engine, async proxy: no generic->async proxy fence in front of the tensor core).
-// Two further conventions let the backward's tensor core produce the softmax arguments directly:
+// Conventions that let the tensor core produce the softmax arguments and row sums directly:
 //   * Q is stored multiplied by (1/sqrt(d)) * log2(e), so S = Q K^T is already in the scaled log2 domain;
 //   * every tile carries ONE extra chunk (index d/8) per row: for Q it holds (-lse_hi, -lse_lo, 0...), for dO
 //     (-D_hi, -D_lo, 0...) as bf16 hi/lo pairs, written by the backward prep kernel.  With K and V extended by a chunk
-//     (1, 1, 0...) the products K' Q'^T = S - lse and V' dO'^T = dP - D need no per-element correction.
+//     (1, 1, 0...) the products K' Q'^T = S - lse and V' dO'^T = dP - D need no per-element correction;
+//   * V's extra chunk is (1, 0...) for real keys (0 for padding): P V' returns the row sum of P in column d.  K's is 0.
 __host__ __device__ __forceinline__ int64_t pad128(int64_t S) { return (S + 127) / 128 * 128; }
 __host__ __device__ __forceinline__ int64_t tile_elems(int d) { return 128 * (int64_t)(d + 8); }
 __device__ __forceinline__ size_t tiled_off(int64_t head, int64_t S_pad, int64_t s, int d, int ch) {
@@ -64,7 +65,8 @@ __device__ __forceinline__ void rope8(float (&x)[8], int s, int c0, const float*
 
 __global__ void __launch_bounds__(256)
 attn_prep_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t B, int64_t S, int nh, int d,
-                 const float* __restrict__ freqs /* NULL: no rope */, int tiled, float qscale) {
+                 const float* __restrict__ freqs /* NULL: no rope */, int tiled, float qscale,
+                 int extra /* tile's extra chunk: 0 leave, 1 zeros, 2 (1,0...) for rows < S */) {
     const int cpr = d >> 3;                                   // 8-element chunks per head row
     const int64_t Sx = tiled ? pad128(S) : S;
     const int64_t total = B * Sx * nh * cpr;
@@ -87,6 +89,8 @@ attn_prep_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t 
     }
     bf16* out = tiled ? dst + tiled_off(b * nh + h, Sx, s, d, ch) : dst + ((b * nh + h) * S + s) * d + ch * 8;
     *reinterpret_cast<uint4*>(out) = o;
+    if (tiled && extra && ch == 0)
+        *reinterpret_cast<uint4*>(dst + tiled_off(b * nh + h, Sx, s, d, cpr)) = make_uint4((extra == 2 && s < S) ? 0x00003F80u : 0u, 0u, 0u, 0u);
 }
 
 // fused-projection variant: qkv bf16 [B*S, ld] (columns: H*d of q | Hkv*d of k | Hkv*d of v, the output of
@@ -108,15 +112,17 @@ attn_pack_qkv_kernel(const bf16* __restrict__ qkv, int64_t ld, bf16* __restrict_
     const int hh = (int)((idx / cpr) % nh);
     const int64_t s = (idx / ((int64_t)cpr * nh)) % Sp;
     const int64_t b = idx / ((int64_t)cpr * nh * Sp);
-    if (s >= S) {                                             // padding rows exist only in the pre-tiled Q
-        if (hh < H) *reinterpret_cast<uint4*>(Qb + tiled_off(b * H + hh, Sp, s, d, ch)) = make_uint4(0u, 0u, 0u, 0u);
+    bf16* dst; bool rope; int extra;                           // extra chunk: 0 leave (Q: written by the backward prep), 1 zeros, 2 (1,0...)
+    if (hh < H) { dst = Qb + tiled_off(b * H + hh, Sp, s, d, ch); rope = true; extra = 0; }
+    else if (hh < H + Hkv) { dst = Kb + tiled_off(b * Hkv + (hh - H), Sp, s, d, ch); rope = true; extra = 1; }
+    else { dst = Vb + tiled_off(b * Hkv + (hh - H - Hkv), Sp, s, d, ch); rope = false; extra = 2; }
+    if (extra && ch == 0)
+        *reinterpret_cast<uint4*>(dst + (size_t)cpr * (128 * 8)) = make_uint4((extra == 2 && s < S) ? 0x00003F80u : 0u, 0u, 0u, 0u);
+    if (s >= S) {                                             // padding rows of the tiles are zero
+        *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
         return;
     }
     const uint4 raw = __ldg(reinterpret_cast<const uint4*>(qkv + (b * S + s) * ld + (int64_t)hh * d + ch * 8));
-    bf16* dst; bool rope;
-    if (hh < H) { dst = Qb + tiled_off(b * H + hh, Sp, s, d, ch); rope = true; }
-    else if (hh < H + Hkv) { dst = Kb + ((b * Hkv + (hh - H)) * S + s) * d + ch * 8; rope = true; }
-    else { dst = Vb + ((b * Hkv + (hh - H - Hkv)) * S + s) * d + ch * 8; rope = false; }
     uint4 o = raw;
     if ((rope && freqs) || hh < H) {
         float x[8];
@@ -331,8 +337,8 @@ attn_fwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
     const int kvh = h / (H / Hkv);
     const int q = q0 + tid;
     const bool valid_q = q < S;
-    const bf16* Kbase = Kb + ((size_t)(b * Hkv + kvh) * S) * D;
-    const bf16* Vbase = Vb + ((size_t)(b * Hkv + kvh) * S) * D;
+    const bf16* Kbase = Kb + (size_t)(b * Hkv + kvh) * (pad128(S) >> 7) * tile_elems(D);   // pre-tiled operands
+    const bf16* Vbase = Vb + (size_t)(b * Hkv + kvh) * (pad128(S) >> 7) * tile_elems(D);
     const int nkv = (S + 127) / 128;
 
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, 256);
@@ -343,9 +349,9 @@ attn_fwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
         load_row_tiled<D>(Qb + (size_t)(b * H + h) * (pad128(S) >> 7) * tile_elems(D), valid_q ? q : 0, valid_q, r);
         store_row<D>(Qs, tid, r);
         const bool vk = tid < S;
-        load_row<D>(Kbase + (size_t)(vk ? tid : 0) * D, vk, r);
+        load_row_tiled<D>(Kbase, vk ? tid : 0, vk, r);
         store_row<D>(Ks, tid, r);
-        load_row<D>(Vbase + (size_t)(vk ? tid : 0) * D, vk, r);
+        load_row_tiled<D>(Vbase, vk ? tid : 0, vk, r);
         store_row<D>(Vs, tid, r);
 #pragma unroll
         for (int bb = 0; bb < 2; ++bb) {                // constant ones / zero chunks (bf16 1.0 = 0x3F80)
@@ -355,8 +361,8 @@ attn_fwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
         if (nkv > 1) {
             const int kn = 128 + tid;
             const bool v1 = kn < S;
-            load_row<D>(Kbase + (size_t)(v1 ? kn : 0) * D, v1, kreg);
-            load_row<D>(Vbase + (size_t)(v1 ? kn : 0) * D, v1, vreg);
+            load_row_tiled<D>(Kbase, v1 ? kn : 0, v1, kreg);
+            load_row_tiled<D>(Vbase, v1 ? kn : 0, v1, vreg);
         }
     }
     tc::fence_async_smem();
@@ -418,8 +424,8 @@ attn_fwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
         if (j + 2 < nkv) {                              // start fetching tile j+2
             const int kn = (j + 2) * 128 + tid;
             const bool vk = kn < S;
-            load_row<D>(Kbase + (size_t)(vk ? kn : 0) * D, vk, kreg);
-            load_row<D>(Vbase + (size_t)(vk ? kn : 0) * D, vk, vreg);
+            load_row_tiled<D>(Kbase, vk ? kn : 0, vk, kreg);
+            load_row_tiled<D>(Vbase, vk ? kn : 0, vk, vreg);
         }
         float sv[128];
         {
@@ -564,8 +570,7 @@ attn_bwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
     float nstat = 0.f;
     {
         uint4 r[D / 8];
-        const bf16* base = (half == 0 ? Kb : Vb) + ((size_t)(b * Hkv + kvh) * S + (valid_k ? key : 0)) * D;
-        load_row<D>(base, valid_k, r);
+        load_row_tiled<D>((half == 0 ? Kb : Vb) + (size_t)(b * Hkv + kvh) * (pad128(S) >> 7) * tile_elems(D), valid_k ? key : 0, valid_k, r);
         store_row<D>(half == 0 ? Kt : Vt, row, r);
         const bool vq = row < S;                     // query tile 0 -> buffer 0
         load_row_tiled<D>(tile_src, vq ? row : 0, vq, r);
@@ -839,7 +844,7 @@ attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const
         const int row = tid & 127, which = tid >> 7;
         const bool vk = k0 + row < S;
         uint4 r[D / 8];
-        load_row<D>((which == 0 ? Kb : Vb) + ((size_t)(b * Hkv + kvh) * S + (vk ? k0 + row : 0)) * D, vk, r);
+        load_row_tiled<D>((which == 0 ? Kb : Vb) + (size_t)(b * Hkv + kvh) * nq * tile_elems(D), vk ? k0 + row : 0, vk, r);
         uint8_t* tile = sm + (which == 0 ? OFF_K : OFF_V);
         store_row<D>(tile, row, r);
         *reinterpret_cast<uint4*>(tile + 4 * (128 * 16) + row * 16) = make_uint4(0x3F803F80u, 0u, 0u, 0u);   // (1, 1, 0...)
@@ -1086,12 +1091,12 @@ struct AttnWs {
     float *Dvec, *dQacc, *dKh, *dVh;
 };
 static size_t attn_ws_bytes(int64_t B, int64_t S, int H, int Hkv, int d) {
-    const size_t qe = (size_t)B * H * S * d, ke = (size_t)B * Hkv * S * d, qp = (size_t)B * H * pad128(S) * (d + 8);
+    const size_t qe = (size_t)B * H * S * d, ke = (size_t)B * Hkv * pad128(S) * (d + 8), qp = (size_t)B * H * pad128(S) * (d + 8);
     return align_up(qp * 2) * 2 + align_up(ke * 2) * 2 + align_up((size_t)B * H * S * 4) + 3 * align_up(qe * 4) + 1024;
 }
 static bool attn_carve(AttnWs& w, void* ws, size_t bytes, int64_t B, int64_t S, int H, int Hkv, int d) {
     Arena ar(ws, bytes);
-    const size_t qe = (size_t)B * H * S * d, ke = (size_t)B * Hkv * S * d, qp = (size_t)B * H * pad128(S) * (d + 8);
+    const size_t qe = (size_t)B * H * S * d, ke = (size_t)B * Hkv * pad128(S) * (d + 8), qp = (size_t)B * H * pad128(S) * (d + 8);
     w.Qb = ar.take<bf16>(qp); w.Kb = ar.take<bf16>(ke); w.Vb = ar.take<bf16>(ke); w.dOb = ar.take<bf16>(qp);
     w.Dvec = ar.take<float>((size_t)B * H * S);
     w.dQacc = ar.take<float>(qe); w.dKh = ar.take<float>(qe); w.dVh = ar.take<float>(qe);
@@ -1107,11 +1112,11 @@ static inline unsigned nb256(int64_t n) { return (unsigned)((n + 255) / 256); }
 
 static int attn_prep_all(const float* q, const float* k, const float* v, const AttnWs& w, int64_t B, int64_t S,
                          int H, int Hkv, int d, const float* freqs, cudaStream_t st) {
-    attn_prep_kernel<<<nb256(B * pad128(S) * H * (d / 8)), 256, 0, st>>>(q, w.Qb, B, S, H, d, freqs, 1, (1.0f / sqrtf((float)d)) * 1.4426950408889634f);
+    attn_prep_kernel<<<nb256(B * pad128(S) * H * (d / 8)), 256, 0, st>>>(q, w.Qb, B, S, H, d, freqs, 1, (1.0f / sqrtf((float)d)) * 1.4426950408889634f, 0);
     GAOT_LAUNCH_CHECK();
-    attn_prep_kernel<<<nb256(B * S * Hkv * (d / 8)), 256, 0, st>>>(k, w.Kb, B, S, Hkv, d, freqs, 0, 1.0f);
+    attn_prep_kernel<<<nb256(B * pad128(S) * Hkv * (d / 8)), 256, 0, st>>>(k, w.Kb, B, S, Hkv, d, freqs, 1, 1.0f, 1);
     GAOT_LAUNCH_CHECK();
-    attn_prep_kernel<<<nb256(B * S * Hkv * (d / 8)), 256, 0, st>>>(v, w.Vb, B, S, Hkv, d, nullptr, 0, 1.0f);
+    attn_prep_kernel<<<nb256(B * pad128(S) * Hkv * (d / 8)), 256, 0, st>>>(v, w.Vb, B, S, Hkv, d, nullptr, 1, 1.0f, 2);
     GAOT_LAUNCH_CHECK();
     return GAOT_OK;
 }
@@ -1237,13 +1242,13 @@ int gaot_attn_backward(const float* q, const float* k, const float* v, const flo
 
 // ---- fused-block flavour: operands stay in the kernels' own bf16 per-head layout between forward and backward ----
 size_t gaot_attn_packed_bytes(int64_t B, int64_t S, int32_t H, int32_t Hkv, int32_t d) {
-    return align_up((size_t)B * H * pad128(S) * (d + 8) * 2) + 2 * align_up((size_t)B * Hkv * S * d * 2);
+    return align_up((size_t)B * H * pad128(S) * (d + 8) * 2) + 2 * align_up((size_t)B * Hkv * pad128(S) * (d + 8) * 2);
 }
 
 static void attn_packed_ptrs(AttnWs& w, void* packed, int64_t B, int64_t S, int H, int Hkv, int d) {
     char* p = (char*)packed;
     w.Qb = (bf16*)p; p += align_up((size_t)B * H * pad128(S) * (d + 8) * 2);
-    w.Kb = (bf16*)p; p += align_up((size_t)B * Hkv * S * d * 2);
+    w.Kb = (bf16*)p; p += align_up((size_t)B * Hkv * pad128(S) * (d + 8) * 2);
     w.Vb = (bf16*)p;
 }
 
