@@ -524,6 +524,246 @@ attn_fwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
     if (warp == 0) tc::tmem_dealloc(tmem, 256);
 }
 
+// --------------------------------------------------------------------------- forward, warp-specialised (head_dim 32)
+// One CTA per SM owns 128 queries of one (batch, head) and walks the 128-key tiles.  The scores of a tile live in one
+// of TWO TMEM stages, so the tensor core computes S of tile j+2 while the softmax warps work on tile j+1 and the P V
+// products of tile j drain behind them; no CTA-wide barrier in the loop, the roles talk through mbarriers.
+//   softmax warps (16): warp = (lane quarter q4, key group g): each thread owns ONE query row and the 32 keys of group g
+//       of every tile -- four independent online-softmax streams per row, so no cross-warp max exchange.  Per tile:
+//       tcgen05.ld 32 scores -> max -> P = exp2(S - m) -> bf16 pairs -> tcgen05.st INTO THE SAME TMEM COLUMNS (P aliases
+//       S: only this thread ever reads those S values) -> arrive.  No shared-memory traffic, no proxy fence.
+//       The stream's running output O_g stays in TMEM for the whole kernel; the reference max m is only raised when the
+//       tile max exceeds it by more than 2^8 (the result is invariant to m; P <= 256 is harmless in bf16 / fp32), in
+//       which case the warp rescales its O_g rows in place (tcgen05.ld / st) after the previous P V has completed.
+//   MMA warp (1 lane): wait softmax(j) -> O_g += P_g V_g (A operand from TMEM, V' carries a ones column: column 32 of
+//       O_g is the row sum) -> commit(pv) -> S(j+2) = Q K^T into the stage just consumed -> commit(S).
+//   loader warp: one cp.async.bulk per pre-tiled K / V tile, three tiles deep, released by the P V barrier.
+// End: the four streams of a row are merged through shared memory (max, rescale, sum), out = O / l, lse = m + log2 l.
+// TMEM (512 columns): S / P stage s at 128 s (P_g at +32 g, 16 packed columns); O_g at 256 + 48 g.
+namespace fw2 {
+constexpr int D = 32, NST = 3;
+constexpr int KT_B = 128 * D * 2;                   // 8 KB  K tile (the data chunks only)
+constexpr int VT_B = 128 * (D + 16) * 2;            // 12 KB V' tile: 32 + ones chunk + zero chunk
+constexpr int T_G = 128 * (D + 8) * 2;              // 10 KB: a pre-tiled operand tile in global memory
+constexpr int OFF_Q = 0, OFF_K = KT_B, OFF_V = OFF_K + NST * KT_B, END_RING = OFF_V + NST * VT_B;   // 69632
+constexpr int MERGE_B = 4 * 128 * 33 * 4 + 128 * 4 * 4;                                             // 69632
+constexpr int SMEM = (END_RING > KT_B + MERGE_B ? END_RING : KT_B + MERGE_B);
+constexpr uint32_t TM_O = 256;
+constexpr float TAU = 8.0f;
+constexpr int NSW = 16;                             // softmax warps
+constexpr int W_MMA = NSW, W_LOAD = NSW + 1, THREADS = (NSW + 2) * 32;
+}
+
+template <bool DROP>
+__global__ void __launch_bounds__(fw2::THREADS, 1)
+attn_fwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const bf16* __restrict__ Vb,
+                 void* __restrict__ out_v, int out_bf16, float* __restrict__ out32, float* __restrict__ lse,
+                 int S, int H, int Hkv, const DropCfg dc) {
+    using namespace fw2;
+    extern __shared__ __align__(1024) uint8_t sm[];
+    __shared__ uint64_t bar_S[2], bar_sm[2], bar_pv, bar_load[NST];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 128;
+    const int kvh = h / (H / Hkv);
+    const int nkv = (S + 127) / 128;
+
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+    if (tid == 32) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&bar_S[i], 1); tc::mbar_init(&bar_sm[i], NSW); }
+        tc::mbar_init(&bar_pv, 1);
+#pragma unroll
+        for (int i = 0; i < NST; ++i) tc::mbar_init(&bar_load[i], 1);
+        tc::mbar_fence_init();
+    }
+    if (tid < 128 * NST) {                            // the zero chunk of every V' buffer (never overwritten)
+        const int row = tid & 127, bf = tid >> 7;
+        *reinterpret_cast<uint4*>(sm + OFF_V + bf * VT_B + 5 * (128 * 16) + row * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t sbase = tc::smem_u32(sm);
+
+    if (warp == W_LOAD) {
+        // ------------------------------------------------------------------ loader
+        if (lane == 0) {
+            const bf16* qsrc = Qb + ((size_t)(b * H + h) * nkv + blockIdx.x) * (T_G / 2);
+            const bf16* ksrc = Kb + (size_t)(b * Hkv + kvh) * nkv * (T_G / 2);
+            const bf16* vsrc = Vb + (size_t)(b * Hkv + kvh) * nkv * (T_G / 2);
+            for (int t = 0; t < nkv; ++t) {
+                const int buf = t % NST;
+                if (t >= NST) tc::mbar_wait(&bar_pv, (uint32_t)((t - NST) & 1));     // P V of the tile that used the buffer is done
+                tc::mbar_arrive_expect_tx(&bar_load[buf], (t == 0 ? KT_B : 0) + KT_B + T_G);
+                if (t == 0) tc::bulk_copy_g2s(sbase + OFF_Q, qsrc, KT_B, &bar_load[buf]);
+                tc::bulk_copy_g2s(sbase + OFF_K + buf * KT_B, ksrc + (size_t)t * (T_G / 2), KT_B, &bar_load[buf]);
+                tc::bulk_copy_g2s(sbase + OFF_V + buf * VT_B, vsrc + (size_t)t * (T_G / 2), T_G, &bar_load[buf]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == W_MMA) {
+        // ------------------------------------------------------------------ tensor-core issue (one lane)
+        if (tc::elect_one()) {
+            constexpr uint32_t idescS = tc::make_idesc_bf16(128, 128, 0, 0);
+            constexpr uint32_t idescPV = tc::make_idesc_bf16(128, D + 16, 0, 1);   // A from TMEM (K-major), B = V' MN-major
+            constexpr uint32_t KS = tc::kstep_kmajor(128);
+            const tc::Desc dQ_ = tc::kmajor(sbase + OFF_Q, 128);
+            const tc::Desc dK_ = tc::kmajor(sbase + OFF_K, 128);
+            const tc::Desc dV_ = tc::mnmajor(sbase + OFF_V, 128);
+            auto issue_S = [&](int j) {
+                const uint32_t off = (j % NST) * KT_B;
+#pragma unroll
+                for (int k = 0; k < D / 16; ++k)
+                    tc::mma_bf16(tmem + (uint32_t)(j & 1) * 128u, dQ_.adv(k * KS).u64(), dK_.adv(off + k * KS).u64(), idescS, k > 0);
+            };
+            tc::mbar_wait(&bar_load[0], 0);
+            issue_S(0); tc::mma_commit(&bar_S[0]);
+            if (nkv > 1) { tc::mbar_wait(&bar_load[1], 0); issue_S(1); tc::mma_commit(&bar_S[1]); }
+            for (int j = 0; j < nkv; ++j) {
+                const int s = j & 1;
+                tc::mbar_wait(&bar_sm[s], (uint32_t)((j >> 1) & 1));             // P(j) is in TMEM, the stage's S has been read
+                tc::fence_after_sync();
+                const uint32_t voff = (j % NST) * VT_B;
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)     // O_g[q, 0..47] += P_g[q, 16 keys] V'[16 keys, 0..47]
+                        tc::mma_bf16_ts(tmem + TM_O + 48u * g, tmem + (uint32_t)s * 128u + 32u * g + 8u * k,
+                                        dV_.adv(voff + (g * 2 + k) * tc::KSTEP_MN).u64(), idescPV, (j | k) != 0);
+                tc::mma_commit(&bar_pv);
+                if (j + 2 < nkv) {
+                    tc::mbar_wait(&bar_load[(j + 2) % NST], (uint32_t)(((j + 2) / NST) & 1));
+                    issue_S(j + 2);                 // overwrites the stage P(j) lives in: ordered behind the P V above
+                    tc::mma_commit(&bar_S[s]);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ softmax warps
+        const int q4 = warp & 3, g = warp >> 2;
+        const int row = q4 * 32 + lane, q = q0 + row;
+        const uint32_t tlane = tmem + ((uint32_t)(q4 * 32) << 16);
+        const uint32_t tO = tlane + TM_O + 48u * g;
+        const uint32_t rowkey = DROP ? drop_rowkey(dc, (uint32_t)((b * H + h) * S + q)) : 0u;
+        float m_used = -INFINITY, l_reg = 0.f;
+        for (int j = 0; j < nkv; ++j) {
+            const int s = j & 1;
+            const uint32_t tS = tlane + (uint32_t)s * 128u + 32u * g;
+            tc::mbar_wait(&bar_S[s], (uint32_t)((j >> 1) & 1));
+            tc::fence_after_sync();
+            float sv[32];
+            tc::tmem_ld32(tS, sv);
+            const int kvalid = S - (j * 128 + g * 32);   // keys >= kvalid of this group are padding
+            if (kvalid < 32) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) if (c >= kvalid) sv[c] = -INFINITY;
+            }
+            float mt = fmax3(sv[0], sv[1], sv[2]);
+#pragma unroll
+            for (int c = 3; c + 1 < 32; c += 2) mt = fmax3(mt, sv[c], sv[c + 1]);
+            mt = fmaxf(mt, sv[31]);
+            const bool raise = mt > m_used + TAU;        // also true on the first tile with a real key (m_used = -inf)
+            if (__any_sync(0xffffffffu, raise)) {
+                if (j > 0) {                             // rescale this warp's O_g rows in place (rare after the first tiles)
+                    tc::mbar_wait(&bar_pv, (uint32_t)((j - 1) & 1));
+                    tc::fence_after_sync();
+                    const float f = raise ? ex2_approx(m_used - mt) : 1.0f;      // m_used = -inf -> 0 (O_g is still all zero)
+                    uint32_t o[32], o32;
+                    tc::tmem_ld32_nowait(tO, o);
+                    tc::tmem_ld1_nowait(tO + 32, o32);
+                    tc::tmem_wait_ld();
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * f);
+                    tc::tmem_st32(tO, o);
+                    tc::tmem_st1(tO + 32, __float_as_uint(__uint_as_float(o32) * f));
+                    if (DROP) l_reg *= f;
+                }
+                if (raise) m_used = mt;
+            }
+            const float nm = (m_used == -INFINITY) ? 0.f : -m_used;             // all keys so far padding: exp2(-inf) = 0
+            uint32_t pk[16];
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+                float p0 = ex2_approx(sv[c] + nm), p1 = ex2_approx(sv[c + 1] + nm);
+                if (DROP) {
+                    l_reg += p0 + p1;
+                    const uint32_t kk = (uint32_t)(j * 128 + g * 32 + c);
+                    p0 = drop_keep(dc, rowkey, kk) ? p0 * dc.inv_keep : 0.f;
+                    p1 = drop_keep(dc, rowkey, kk + 1) ? p1 * dc.inv_keep : 0.f;
+                }
+                pk[c >> 1] = tc::pack_bf16(p0, p1);
+            }
+            tc::tmem_st16(tS, pk);
+            tc::tmem_wait_st();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&bar_sm[s]);
+        }
+        // ---- merge the four streams of each row ----
+        tc::mbar_wait(&bar_pv, (uint32_t)((nkv - 1) & 1));
+        tc::fence_after_sync();
+        float* mbuf = reinterpret_cast<float*>(sm + KT_B);              // [128][4] stream maxima
+        float* obuf = mbuf + 128 * 4;                                   // [4][128][33] rescaled stream outputs (+ row sum)
+        mbuf[row * 4 + g] = m_used;
+        asm volatile("bar.sync 1, %0;\n" ::"n"(NSW * 32) : "memory");
+        const float4 m4 = *reinterpret_cast<const float4*>(mbuf + row * 4);
+        const float m = fmaxf(fmaxf(m4.x, m4.y), fmaxf(m4.z, m4.w));
+        const float f = (m_used == -INFINITY) ? 0.f : ex2_approx(m_used - m);
+        {
+            uint32_t o[32], o32;
+            tc::tmem_ld32_nowait(tO, o);
+            tc::tmem_ld1_nowait(tO + 32, o32);
+            tc::tmem_wait_ld();
+            float* dst = obuf + (size_t)(g * 128 + row) * 33;
+            if (m_used == -INFINITY) {                                  // the stream never saw a real key: O_g was never written
+#pragma unroll
+                for (int c = 0; c < 33; ++c) dst[c] = 0.f;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) dst[c] = __uint_as_float(o[c]) * f;
+                dst[32] = (DROP ? l_reg : __uint_as_float(o32)) * f;
+            }
+        }
+        asm volatile("bar.sync 1, %0;\n" ::"n"(NSW * 32) : "memory");
+        if (q < S) {
+            float l = 0.f, acc[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+#pragma unroll
+            for (int gg = 0; gg < 4; ++gg) {
+                const float* src = obuf + (size_t)(gg * 128 + row) * 33;
+                l += src[32];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[c] += src[g * 8 + c];
+            }
+            const float inv = 1.0f / l;
+            const size_t ooff = ((size_t)b * S + q) * (H * D) + h * D + g * 8;
+            if (out_bf16) {
+                uint4 pk;
+                pk.x = tc::pack_bf16(acc[0] * inv, acc[1] * inv); pk.y = tc::pack_bf16(acc[2] * inv, acc[3] * inv);
+                pk.z = tc::pack_bf16(acc[4] * inv, acc[5] * inv); pk.w = tc::pack_bf16(acc[6] * inv, acc[7] * inv);
+                *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(out_v) + ooff) = pk;
+                if (out32) {
+                    *reinterpret_cast<float4*>(out32 + ooff) = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+                    *reinterpret_cast<float4*>(out32 + ooff + 4) = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
+                }
+            } else {
+                float* o = reinterpret_cast<float*>(out_v) + ooff;
+                *reinterpret_cast<float4*>(o) = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+                *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
+            }
+            if (g == 0) lse[((size_t)b * H + h) * S + q] = m + log2f(l);
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
 // --------------------------------------------------------------------------- backward
 // CTA = 128 keys of one (batch, head), 256 threads, loop over 128-query tiles processed as two
 // 64-query halves so that the TMEM footprint (S^T 64 + dP^T 64 + dV + dK + dQ columns) fits 256
@@ -1148,6 +1388,19 @@ static int attn_launch_fwd(const AttnWs& w, int64_t B, int64_t S, int H, int Hkv
     const bool drop = dropout_p > 0.f;
     dim3 grid((unsigned)((S + 127) / 128), (unsigned)H, (unsigned)B);
     GAOT_TIME_KERNEL("attn_fwd", st, 4.0 * (double)B * H * (double)S * (double)S * d);
+    const char* dbg_env = getenv("GAOT_ATTN_DEBUG");
+    const int dbg = dbg_env ? atoi(dbg_env) : 0;
+    if (d == 32 && !(dbg & 64)) {                    // warp-specialised kernel (GAOT_ATTN_DEBUG bit 6 selects the older one)
+        if (drop) {
+            GAOT_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fw2::SMEM));
+            attn_fwd2_kernel<true><<<grid, fw2::THREADS, fw2::SMEM, st>>>(w.Qb, w.Kb, w.Vb, out, out_bf16, out32, lse, (int)S, H, Hkv, dc);
+        } else {
+            GAOT_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fw2::SMEM));
+            attn_fwd2_kernel<false><<<grid, fw2::THREADS, fw2::SMEM, st>>>(w.Qb, w.Kb, w.Vb, out, out_bf16, out32, lse, (int)S, H, Hkv, dc);
+        }
+        GAOT_LAUNCH_CHECK();
+        return GAOT_OK;
+    }
 #define GAOT_FWD_LAUNCH(DD, DR, SM)                                                                                   \
     do { GAOT_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DD, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM))); \
          attn_fwd_kernel<DD, DR><<<grid, 128, (SM), st>>>(w.Qb, w.Kb, w.Vb, out, out_bf16, out32, lse, (int)S, H, Hkv, dc); } while (0)
