@@ -4,7 +4,7 @@
 // with allow_tf32 = False those run on the FP32 SIMT pipe (~30 ms of a 70 ms step at S = 16384).
 //
 // One kernel, C[M,N] = sum_k A(m,k) * B(n,k), BF16 operands / FP32 accumulation in TMEM.  Operands
-// stay in their natural row-major global layout; the loader converts fp32 -> bf16 on the fly and writes
+// stay in their natural row-major global layout; the loader (LDG -> registers -> STS; fp32 converted on the fly) writes
 // "chunk-major" shared tiles (tc05.cuh) that serve as K-major or MN-major tensor-core operands, so the
 // three products of a linear layer need no transposed copies:
 //     forward   y  = x  W^T     A = x  [M,K]  K-major     B = W [N,K]  K-major
@@ -12,7 +12,8 @@
 //     d weight  dW = dy^T x     A = dy [M,N]  MN-major    B = x [M,K]  MN-major (contraction over M, split-K)
 // CTA = 128x128 output tile, 256 threads: all threads stage operands (coalesced float4 loads, 8-byte
 // conflict-free shared stores into slabs padded by 16 B), one elected thread issues tcgen05.mma
-// (4 x K16 per 64-deep block) into a 3-stage ring released by tcgen05.commit -> mbarrier; 2 CTAs/SM.
+// (4 x K16 per 64-deep block) into a 3-stage ring released by tcgen05.commit -> mbarrier; 2 CTAs/SM.  (The bf16
+// forward / d-input products normally run on the persistent gemm2 kernel further down.)
 // Epilogue: tcgen05.ld -> warp-private XOR-swizzled transpose -> coalesced 128 B row segments with
 // fused bias / residual / accumulate, fp32 or bf16 output.
 #include "common.cuh"
@@ -84,31 +85,33 @@ template <bool MN> struct Stager<float, MN> {
     }
 };
 
-// bf16 sources need no conversion: cp.async (LDGSTS) lands 16-byte chunks directly in the tile, so several
-// K blocks stay in flight without holding registers (src-size 0 zero-fills out-of-range chunks).
-__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr, bool valid) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(saddr), "l"(gptr), "r"(valid ? 16u : 0u) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
-template <bool MN>
-__device__ __forceinline__ void stage_async(const bf16* __restrict__ src, int64_t ld, int64_t row0, int64_t col0,
-                                            int64_t row_lim, int64_t col_lim, uint32_t tile_saddr, int tid) {
-    constexpr int CH_PER_ROW = MN ? 16 : 8;
-    constexpr int ROWS_PER_PASS = dn::THREADS / CH_PER_ROW;
-    constexpr uint32_t SLAB = MN ? dn::SLAB_MN : dn::SLAB_K;
-    const int ch = tid % CH_PER_ROW, rr = tid / CH_PER_ROW;
-    const int64_t col = col0 + ch * 8;
-    const uint32_t base = tile_saddr + ch * SLAB;
+// bf16 sources need no conversion, but they are register-staged too (LDG.128 -> STS.128): cp.async (LDGSTS) with
+// 16-byte pieces scattered over the padded slabs sustains only one warp instruction per ~150 cycles (measured on B200),
+// which made every bf16 product loader-bound.
+template <bool MN> struct Stager<bf16, MN> {
+    uint4 r[4];
+    __device__ __forceinline__ void load(const bf16* __restrict__ src, int64_t ld, int64_t row0, int64_t col0,
+                                         int64_t row_lim, int64_t col_lim, int tid) {
+        constexpr int CH_PER_ROW = MN ? 16 : 8;
+        constexpr int ROWS_PER_PASS = dn::THREADS / CH_PER_ROW;
+        const int ch = tid % CH_PER_ROW, rr = tid / CH_PER_ROW;
+        const int64_t col = col0 + ch * 8;
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        const int r = p * ROWS_PER_PASS + rr;
-        const int64_t row = row0 + r;
-        const bool ok = row < row_lim && col < col_lim;
-        cp_async16(base + r * 16, ok ? (const void*)(src + row * ld + col) : (const void*)src, ok);
+        for (int p = 0; p < 4; ++p) {
+            const int64_t row = row0 + p * ROWS_PER_PASS + rr;
+            r[p] = (row < row_lim && col < col_lim) ? __ldg(reinterpret_cast<const uint4*>(src + row * ld + col)) : make_uint4(0u, 0u, 0u, 0u);
+        }
     }
-}
+    __device__ __forceinline__ void store(uint8_t* tile, int tid) const {
+        constexpr int CH_PER_ROW = MN ? 16 : 8;
+        constexpr int ROWS_PER_PASS = dn::THREADS / CH_PER_ROW;
+        constexpr uint32_t SLAB = MN ? dn::SLAB_MN : dn::SLAB_K;
+        const int ch = tid % CH_PER_ROW, rr = tid / CH_PER_ROW;
+        uint8_t* base = tile + ch * SLAB;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) *reinterpret_cast<uint4*>(base + (p * ROWS_PER_PASS + rr) * 16) = r[p];
+    }
+};
 
 template <typename T> struct is_bf16 { static constexpr bool value = false; };
 template <> struct is_bf16<bf16> { static constexpr bool value = true; };
@@ -138,69 +141,30 @@ gemm_tc_kernel(const GemmArgs g) {
     tc::fence_after_sync();
     const uint32_t tmem = tmem_base_s;
 
-    constexpr bool A_ASYNC = is_bf16<TA>::value, B_ASYNC = is_bf16<TB>::value;
     constexpr uint32_t idesc = tc::make_idesc_bf16(dn::BM, dn::BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     constexpr uint32_t A_LBO = A_MN ? 128u : dn::SLAB_K, A_SBO = A_MN ? dn::SLAB_MN : 128u, A_KSTEP = A_MN ? 256u : 2u * dn::SLAB_K;
     constexpr uint32_t B_LBO = B_MN ? 128u : dn::SLAB_K, B_SBO = B_MN ? dn::SLAB_MN : 128u, B_KSTEP = B_MN ? 256u : 2u * dn::SLAB_K;
     const uint32_t sm_base = tc::smem_u32(sm);
 
-    // register-staged path (fp32 sources, converted on the fly): one K block ahead
-    Stager<float, A_MN> sa;
-    Stager<float, B_MN> sb;
+    // register-staged operands (fp32 converted on the fly, bf16 copied): one K block ahead
+    Stager<TA, A_MN> sa;
+    Stager<TB, B_MN> sb;
     auto fetch_regs = [&](int kb) {
         const int64_t k0 = (int64_t)(kb0 + kb) * dn::BK;
-        if constexpr (!A_ASYNC) {
-            if (A_MN) sa.load((const float*)g.A, g.lda, k0, m0, g.K, g.M, tid);
-            else if (k0 < g.k_split) sa.load((const float*)g.A, g.lda, m0, k0, g.M, g.k_split, tid);
-            else sa.load((const float*)g.A2, g.lda2, m0, k0 - g.k_split, g.M, g.K - g.k_split, tid);
-        }
-        if constexpr (!B_ASYNC) {
-            if (B_MN) sb.load((const float*)g.B, g.ldb, k0, n0, g.K, g.N, tid);
-            else      sb.load((const float*)g.B, g.ldb, n0, k0, g.N, g.K, tid);
-        }
+        if (A_MN) sa.load((const TA*)g.A, g.lda, k0, m0, g.K, g.M, tid);
+        else if (k0 < g.k_split) sa.load((const TA*)g.A, g.lda, m0, k0, g.M, g.k_split, tid);
+        else sa.load((const TA*)g.A2, g.lda2, m0, k0 - g.k_split, g.M, g.K - g.k_split, tid);
+        if (B_MN) sb.load((const TB*)g.B, g.ldb, k0, n0, g.K, g.N, tid);
+        else      sb.load((const TB*)g.B, g.ldb, n0, k0, g.N, g.K, tid);
     };
-    // cp.async path (bf16 sources): STAGES-1 K blocks ahead
-    auto issue_async = [&](int kb) {
-        const int64_t k0 = (int64_t)(kb0 + kb) * dn::BK;
-        const uint32_t st = sm_base + (kb % dn::STAGES) * dn::STAGE_BYTES;
-        if constexpr (A_ASYNC) {
-            if (A_MN) stage_async<true>((const bf16*)g.A, g.lda, k0, m0, g.K, g.M, st, tid);
-            else if (k0 < g.k_split) stage_async<false>((const bf16*)g.A, g.lda, m0, k0, g.M, g.k_split, st, tid);
-            else stage_async<false>((const bf16*)g.A2, g.lda2, m0, k0 - g.k_split, g.M, g.K - g.k_split, st, tid);
-        }
-        if constexpr (B_ASYNC) {
-            if (B_MN) stage_async<true>((const bf16*)g.B, g.ldb, k0, n0, g.K, g.N, st + dn::OP_BYTES, tid);
-            else      stage_async<false>((const bf16*)g.B, g.ldb, n0, k0, g.N, g.K, st + dn::OP_BYTES, tid);
-        }
-    };
-
-    if constexpr (A_ASYNC || B_ASYNC) {
-#pragma unroll
-        for (int p = 0; p < dn::STAGES - 1; ++p) {
-            if (p < nkb) issue_async(p);
-            cp_async_commit();
-        }
-    }
-    if constexpr (!A_ASYNC || !B_ASYNC) { if (nkb > 0) fetch_regs(0); }
+    if (nkb > 0) fetch_regs(0);
     for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % dn::STAGES;
-        // stage (kb-1)%STAGES is re-filled below with block kb+STAGES-1: its previous reader is MMA(kb-1)
-        if constexpr (A_ASYNC || B_ASYNC) {
-            if (kb >= 1) tc::mbar_wait(&mbar_free[(kb - 1) % dn::STAGES], (uint32_t)(((kb - 1) / dn::STAGES) & 1));
-        } else {
-            if (kb >= dn::STAGES) tc::mbar_wait(&mbar_free[s], (uint32_t)((kb / dn::STAGES - 1) & 1));
-        }
-        if constexpr (A_ASYNC || B_ASYNC) {
-            if (kb + dn::STAGES - 1 < nkb) issue_async(kb + dn::STAGES - 1);
-            cp_async_commit();
-        }
-        if constexpr (!A_ASYNC || !B_ASYNC) {
-            uint8_t* stA = sm + s * dn::STAGE_BYTES;
-            if constexpr (!A_ASYNC) sa.store(stA, tid);
-            if constexpr (!B_ASYNC) sb.store(stA + dn::OP_BYTES, tid);
-            if (kb + 1 < nkb) fetch_regs(kb + 1);
-        }
-        if constexpr (A_ASYNC || B_ASYNC) cp_async_wait<dn::STAGES - 1>();
+        if (kb >= dn::STAGES) tc::mbar_wait(&mbar_free[s], (uint32_t)((kb / dn::STAGES - 1) & 1));   // MMA(kb - STAGES) has read the stage
+        uint8_t* stA = sm + s * dn::STAGE_BYTES;
+        sa.store(stA, tid);
+        sb.store(stA + dn::OP_BYTES, tid);
+        if (kb + 1 < nkb) fetch_regs(kb + 1);
         tc::fence_async_smem();
         tc::fence_before_sync();
         __syncthreads();
@@ -282,6 +246,191 @@ gemm_tc_kernel(const GemmArgs g) {
     if (warp == 0) tc::tmem_dealloc(tmem, 128);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// gemm2: persistent, warp-specialised variant for the two products whose A operand is a K-major bf16 activation
+// (forward y = x W^T and d-input dx = dy W).  The one-tile-per-CTA kernel above spends most of its time in its
+// prologue, its per-K-block CTA barrier and an epilogue that nothing overlaps; here a CTA walks a strided list of
+// 128x128 output tiles and the roles never meet at a CTA barrier:
+//   loader warps (6, two per ring stage): LDG.128 -> registers -> STS.128 into the stage's padded chunk-major slabs,
+//       generic->async proxy fence, arrive(full[stage]);  refill after empty[stage]
+//   MMA warp (1 lane): wait full -> 4 x tcgen05.mma (K16) -> commit(empty[stage]); the last K block of a tile also
+//       commits acc_full[buf]; the accumulator is DOUBLE BUFFERED in TMEM (2 x 128 columns), so the next tile's
+//       products start while the epilogue drains this one
+//   epilogue warps (4): wait acc_full[buf] -> tcgen05.ld (32 columns at a time) -> bias / residual -> fp32 or bf16
+//       row segments straight to global -> arrive(acc_empty[buf])
+// 2 CTAs/SM (3 x 32.5 KB ring + 256 TMEM columns each), 12 warps per CTA.
+namespace dn2 {
+constexpr int STAGES = 3, NLOAD = 2 * STAGES, THREADS = 384;
+constexpr int W_MMA = NLOAD, W_EPI = 8;             // warps 0..5 loaders (stage w % 3, half w / 3), 6 MMA, 7 idle, 8..11 epilogue
+constexpr uint32_t SMEM_BYTES = STAGES * dn::STAGE_BYTES;
+}
+
+// half of a stage's operand tile: global (row-major bf16) -> registers (8 x LDG.128 in flight) -> chunk-major shared slab.
+// cp.async (LDGSTS) is NOT used here: with 16-byte pieces scattered over the slabs it sustains one warp instruction per
+// ~150 cycles (measured), an order of magnitude below plain LDG + STS.
+template <bool MN>
+__device__ __forceinline__ void stage_half(const bf16* __restrict__ src, int64_t ld, int64_t row0, int64_t col0,
+                                           int64_t row_lim, int64_t col_lim, uint8_t* tile, int half, int lane) {
+    constexpr int CH = MN ? 16 : 8;                 // 16-byte chunks per tile row
+    constexpr int ROWS_HALF = MN ? 32 : 64;
+    constexpr uint32_t SLAB = MN ? dn::SLAB_MN : dn::SLAB_K;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        uint4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = (b * 8 + j) * 32 + lane;
+            const int r = half * ROWS_HALF + i / CH, ch = i % CH;
+            const int64_t row = row0 + r, col = col0 + ch * 8;
+            v[j] = (row < row_lim && col < col_lim) ? __ldg(reinterpret_cast<const uint4*>(src + row * ld + col)) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = (b * 8 + j) * 32 + lane;
+            const int r = half * ROWS_HALF + i / CH, ch = i % CH;
+            *reinterpret_cast<uint4*>(tile + ch * SLAB + r * 16) = v[j];
+        }
+    }
+}
+
+template <bool B_MN>
+__global__ void __launch_bounds__(dn2::THREADS, 2)
+gemm2_kernel(const GemmArgs g, int tiles_n, int total_tiles) {
+    extern __shared__ __align__(128) uint8_t sm[];
+    __shared__ uint64_t full[dn2::STAGES], empty[dn2::STAGES], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nkb = (int)((g.K + dn::BK - 1) / dn::BK);
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 256);
+    if (tid == 32) {
+#pragma unroll
+        for (int s = 0; s < dn2::STAGES; ++s) { tc::mbar_init(&full[s], 2); tc::mbar_init(&empty[s], 1); }
+#pragma unroll
+        for (int b = 0; b < 2; ++b) { tc::mbar_init(&acc_full[b], 1); tc::mbar_init(&acc_empty[b], 4); }
+        tc::mbar_fence_init();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t sm_base = tc::smem_u32(sm);
+    const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (warp < dn2::NLOAD) {
+        // ------------------------------------------------------------------ loader: ring stage warp % 3, tile half warp / 3
+        const int stg = warp % dn2::STAGES, half = warp / dn2::STAGES;
+        uint8_t* st = sm + stg * dn::STAGE_BYTES;
+        const int total_kb = my_tiles * nkb;          // K blocks are numbered across the CTA's tiles: block G lives in stage G % STAGES
+        for (int G = stg, it = 0; G < total_kb; G += dn2::STAGES, ++it) {
+            const int t = G / nkb, kb = G - t * nkb;
+            const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+            const int64_t m0 = (int64_t)(tile / tiles_n) * dn::BM, n0 = (int64_t)(tile % tiles_n) * dn::BN;
+            if (it > 0) tc::mbar_wait(&empty[stg], (uint32_t)((it - 1) & 1));           // the MMAs that read the stage are done
+            const int64_t k0 = (int64_t)kb * dn::BK;
+            stage_half<false>((const bf16*)g.A, g.lda, m0, k0, g.M, g.K, st, half, lane);
+            if (B_MN) stage_half<true>((const bf16*)g.B, g.ldb, k0, n0, g.K, g.N, st + dn::OP_BYTES, half, lane);
+            else      stage_half<false>((const bf16*)g.B, g.ldb, n0, k0, g.N, g.K, st + dn::OP_BYTES, half, lane);
+            tc::fence_async_smem();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&full[stg]);
+        }
+    } else if (warp == dn2::W_MMA) {
+        // ------------------------------------------------------------------ tensor-core issue (one lane)
+        if (tc::elect_one()) {
+            constexpr uint32_t idesc = tc::make_idesc_bf16(dn::BM, dn::BN, 0, B_MN ? 1 : 0);
+            constexpr uint32_t A_KSTEP = 2u * dn::SLAB_K;
+            constexpr uint32_t B_LBO = B_MN ? 128u : dn::SLAB_K, B_SBO = B_MN ? dn::SLAB_MN : 128u, B_KSTEP = B_MN ? 256u : 2u * dn::SLAB_K;
+            int G = 0;                                // running K-block number (see the loader)
+            for (int t = 0; t < my_tiles; ++t) {
+                const int buf = t & 1;
+                if (t >= 2) { tc::mbar_wait(&acc_empty[buf], (uint32_t)(((t - 2) >> 1) & 1)); tc::fence_after_sync(); }
+                for (int kb = 0; kb < nkb; ++kb, ++G) {
+                    const int s = G % dn2::STAGES;
+                    tc::mbar_wait(&full[s], (uint32_t)((G / dn2::STAGES) & 1));
+                    tc::fence_after_sync();
+                    const tc::Desc dA = tc::make_desc2(sm_base + s * dn::STAGE_BYTES, dn::SLAB_K, 128u);
+                    const tc::Desc dB = tc::make_desc2(sm_base + s * dn::STAGE_BYTES + dn::OP_BYTES, B_LBO, B_SBO);
+#pragma unroll
+                    for (int ks = 0; ks < dn::BK / 16; ++ks)
+                        tc::mma_bf16(tmem + (uint32_t)buf * 128u, dA.adv(ks * A_KSTEP).u64(), dB.adv(ks * B_KSTEP).u64(), idesc, (kb | ks) != 0);
+                    tc::mma_commit(&empty[s]);
+                }
+                tc::mma_commit(&acc_full[buf]);
+            }
+        }
+        __syncwarp();
+    } else if (warp >= dn2::W_EPI) {
+        // ------------------------------------------------------------------ epilogue: lane quarter = warp & 3
+        const int lg = warp & 3;
+        for (int t = 0; t < my_tiles; ++t) {
+            const int tile = (int)blockIdx.x + t * (int)gridDim.x, buf = t & 1;
+            const int64_t m0 = (int64_t)(tile / tiles_n) * dn::BM, n0 = (int64_t)(tile % tiles_n) * dn::BN;
+            const int64_t row = m0 + lg * 32 + lane;
+            tc::mbar_wait(&acc_full[buf], (uint32_t)((t >> 1) & 1));
+            tc::fence_after_sync();
+#pragma unroll 1
+            for (int c0 = 0; c0 < dn::BN; c0 += 32) {
+                float v[32];
+                tc::tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)buf * 128u + c0, v);
+                const int64_t col = n0 + c0;
+                if (row < g.M && col < g.N) {          // N is a multiple of 32 on this path (checked by the host)
+                    if (g.bias) {
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + col + c));
+                            v[c] += b.x; v[c + 1] += b.y; v[c + 2] += b.z; v[c + 3] += b.w;
+                        }
+                    }
+                    if (g.residual) {
+                        const float* rp = g.residual + row * g.ldr + col;
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4) {
+                            const float4 r = __ldg(reinterpret_cast<const float4*>(rp + c));
+                            v[c] += r.x; v[c + 1] += r.y; v[c + 2] += r.z; v[c + 3] += r.w;
+                        }
+                    }
+                    if (g.c_bf16) {
+                        bf16* cp = reinterpret_cast<bf16*>(g.C) + row * g.ldc + col;
+#pragma unroll
+                        for (int c = 0; c < 32; c += 8) {
+                            uint4 o;
+                            o.x = tc::pack_bf16(v[c], v[c + 1]); o.y = tc::pack_bf16(v[c + 2], v[c + 3]);
+                            o.z = tc::pack_bf16(v[c + 4], v[c + 5]); o.w = tc::pack_bf16(v[c + 6], v[c + 7]);
+                            *reinterpret_cast<uint4*>(cp + c) = o;
+                        }
+                    } else {
+                        float* cp = reinterpret_cast<float*>(g.C) + row * g.ldc + col;
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(cp + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+                    }
+                }
+            }
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 256);
+}
+
+template <bool B_MN>
+static int launch_gemm2(const GemmArgs& g, cudaStream_t st) {
+    static bool attr_done = false;
+    auto kern = gemm2_kernel<B_MN>;
+    if (!attr_done) {
+        GAOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dn2::SMEM_BYTES));
+        attr_done = true;
+    }
+    const int tiles_n = (int)((g.N + dn::BN - 1) / dn::BN), tiles_m = (int)((g.M + dn::BM - 1) / dn::BM);
+    const int total = tiles_n * tiles_m;
+    const int grid = std::min(total, 2 * kNumSMs);
+    kern<<<grid, dn2::THREADS, dn2::SMEM_BYTES, st>>>(g, tiles_n, total);
+    GAOT_LAUNCH_CHECK();
+    return GAOT_OK;
+}
+
 // fixed-order sum of the split-K partials (+ bias / accumulate): deterministic weight gradients
 __global__ void __launch_bounds__(256)
 gemm_splitk_reduce_kernel(const float* __restrict__ part, int splits, int64_t M, int64_t N, const float* __restrict__ bias,
@@ -354,6 +503,11 @@ static int run_gemm(GemmArgs g, int a_dtype, int b_dtype, bool a_mn, bool b_mn, 
     }
     GAOT_TIME_KERNEL(timer_name, st, 2.0 * (double)g.M * (double)g.N * (double)g.K);
     int rc;
+    {   // persistent warp-specialised kernel for bf16 K-major-A products (GAOT_GEMM_OLD=1 selects the one-tile kernel)
+        static const bool use_old = getenv("GAOT_GEMM_OLD") && atoi(getenv("GAOT_GEMM_OLD")) != 0;
+        if (!use_old && a_dtype && b_dtype && !a_mn && !g.A2 && !g.accumulate && splits == 1 && g.N % 32 == 0)
+            return b_mn ? launch_gemm2<true>(g, st) : launch_gemm2<false>(g, st);
+    }
     const int sel = (a_dtype ? 8 : 0) | (b_dtype ? 4 : 0) | (a_mn ? 2 : 0) | (b_mn ? 1 : 0);
     switch (sel) {
         case 0:  rc = launch_gemm<float, float, false, false>(g, splits, st); break;
