@@ -1022,9 +1022,10 @@ attn_bwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
 // step n+1, and the accumulator products of step n (dV, dK, dQ) drain behind them.  Nothing in the loop is a CTA-wide
 // barrier; the roles talk through mbarriers:
 //   compute warps (16): wait scores(n) -> tcgen05.ld S'^T, dP'^T (16 columns each) -> P^T = exp2(S'^T),
-//                       dS^T = P^T dP'^T -> bf16 chunk-major tiles -> arrive(cmp[n&1])
-//   MMA warp (1 lane) : wait cmp[n&1] -> scores(n+2) into the stage just read -> commit(S[n&1]);
-//                       dV += P^T dO, dK += dS^T Q, (second half) dQ = dS K -> commit(acc[n&1])
+//                       dS^T = P^T dP'^T -> packed bf16 pairs written back INTO the same TMEM columns (A operands of
+//                       dV / dK); dS^T also to a chunk-major shared tile for dQ -> arrive(cmp[n&1])
+//   MMA warp (1 lane) : wait cmp[n&1] -> dV += P^T dO, dK += dS^T Q (A from TMEM) -> scores(n+2) into the same stage ->
+//                       commit(S[n&1]); (second half) dQ = dS K -> commit(acc[n&1])
 //   drain warps (4)   : wait acc of a tile's second step -> tcgen05.ld dQ (128 queries x 32) -> arrive(dq) -> scaled rows
 //                       to a linear 4 KB staging block -> ONE cp.reduce.async.bulk (.add.f32) per warp into global dQ
 //   loader warp (1)   : one cp.async.bulk per pre-tiled Q / dO tile (10 KB each), three tiles deep, released by the
@@ -1055,7 +1056,8 @@ attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const
                  int S, int H, int Hkv, float scale, float scale_dk, const DropCfg dc) {
     using namespace bw2;
     constexpr int CG = NCW / 4;                      // column groups of a 64-query step
-    constexpr int CPT = 64 / CG;                     // score columns per compute thread (16 or 32)
+    constexpr int CPT = 64 / CG;                     // score columns per compute thread
+    static_assert(NCW == 16, "a thread's 16 queries must be exactly one K16 step of the TMEM A operands");
     constexpr int CQ = D / CG;                       // dK / dV columns per compute thread in the epilogue
     constexpr int W_DRAIN = NCW, W_MMA = NCW + 4, W_LOAD = NCW + 5;
     extern __shared__ __align__(1024) uint8_t sm[];
@@ -1138,7 +1140,7 @@ attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const
             const tc::Desc kK = tc::kmajor(sbase + OFF_K, 128), kV = tc::kmajor(sbase + OFF_V, 128), mK = tc::mnmajor(sbase + OFF_K, 128);
             const tc::Desc kQ = tc::kmajor(sbase + OFF_Q, 128), kdO = tc::kmajor(sbase + OFF_DO, 128);
             const tc::Desc mQ = tc::mnmajor(sbase + OFF_Q, 128), mdO = tc::mnmajor(sbase + OFF_DO, 128);
-            const tc::Desc kPT = tc::kmajor(sbase + OFF_PT, 128), kdS = tc::kmajor(sbase + OFF_DS, 128), mdS = tc::mnmajor(sbase + OFF_DS, 128);
+            const tc::Desc mdS = tc::mnmajor(sbase + OFF_DS, 128);
             auto issue_scores = [&](int n) {          // contraction over 48 columns: 32 + the statistics chunk + a zero chunk
                 const uint32_t off = ((n >> 1) % NLB) * TILE_B + (n & 1) * 64 * 16;
                 const uint32_t tS = tmem + (uint32_t)(n & 1) * 128u;
@@ -1157,18 +1159,19 @@ attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const
                 const int i = n >> 1, hq = n & 1, s = n & 1;
                 tc::mbar_wait(&bar_cmp[s], (uint32_t)((n >> 1) & 1));           // P^T / dS^T of step n written, stage s drained
                 tc::fence_after_sync();
-                if (n + 2 < nsteps) {
+                const uint32_t off = (i % NLB) * TILE_B + hq * 64 * 16;
+                const uint32_t tS = tmem + (uint32_t)s * 128u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)     // dV[key,d] += P^T[key, 16 q] dO[16 q, d]   (A = packed P^T in the stage's S' columns)
+                    tc::mma_bf16_ts(tmem + TM_DV, tS + 16u * k, mdO.adv(off + k * tc::KSTEP_MN).u64(), idescKM, (n | k) != 0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)     // dK[key,d] += dS^T[key, 16 q] Q'[16 q, d]  (A = packed dS^T in the stage's dP' columns)
+                    tc::mma_bf16_ts(tmem + TM_DK, tS + 64u + 16u * k, mQ.adv(off + k * tc::KSTEP_MN).u64(), idescKM, (n | k) != 0);
+                if (n + 2 < nsteps) {             // overwrites the stage the two products above read: ordered behind them
                     if (hq == 0) tc::mbar_wait(&bar_load[(i + 1) % NLB], (uint32_t)(((i + 1) / NLB) & 1));
                     issue_scores(n + 2);
                     tc::mma_commit(&bar_S[s]);
                 }
-                const uint32_t off = (i % NLB) * TILE_B + hq * 64 * 16;
-#pragma unroll
-                for (int k = 0; k < 4; ++k)     // dV[key,d] += P^T[key, 64 q] dO[64 q, d]
-                    tc::mma_bf16(tmem + TM_DV, kPT.adv(s * PT_B + k * KS).u64(), mdO.adv(off + k * tc::KSTEP_MN).u64(), idescKM, (n | k) != 0);
-#pragma unroll
-                for (int k = 0; k < 4; ++k)     // dK[key,d] += dS^T[key, 64 q] Q'[64 q, d]
-                    tc::mma_bf16(tmem + TM_DK, kdS.adv((i & 1) * DS_B + (hq * 4 + k) * KS).u64(), mQ.adv(off + k * tc::KSTEP_MN).u64(), idescKM, (n | k) != 0);
                 if (hq == 1) {
                     if (i >= 2) { tc::mbar_wait(&bar_dq[i & 1], (uint32_t)(((i - 2) >> 1) & 1)); tc::fence_after_sync(); }
 #pragma unroll
@@ -1235,7 +1238,6 @@ attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const
         const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
         const int c0 = cg * CPT;
         const uint32_t kterm = (uint32_t)key * 0x85EBCA6Bu;
-        uint8_t* const pt0 = sm + OFF_PT + (cg * (CPT / 8)) * (128 * 16) + row * 16;
         uint8_t* const ds0 = sm + OFF_DS + (cg * (CPT / 8)) * (128 * 16) + row * 16;
         for (int n = 0; n < nsteps; ++n) {
             const int i = n >> 1, hq = n & 1, s = n & 1;
@@ -1273,14 +1275,22 @@ attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const
                 dk[c8].x = tc::pack_bf16(ds[0], ds[1]); dk[c8].y = tc::pack_bf16(ds[2], ds[3]);
                 dk[c8].z = tc::pack_bf16(ds[4], ds[5]); dk[c8].w = tc::pack_bf16(ds[6], ds[7]);
             }
-            if (n >= 2) tc::mbar_wait(&bar_acc[s], (uint32_t)(((n >> 1) - 1) & 1));   // dV / dK of step n-2 have read P^T[s]
-            uint8_t* pt = pt0 + s * PT_B;
+            // P^T and dS^T go back INTO the TMEM columns their scores came from (this thread owns them) as packed bf16
+            // pairs: they are the A operands of dV / dK.  dS^T also goes to shared memory for dQ = dS K (transposed use).
+            {
+                uint32_t a[CPT / 2];
+#pragma unroll
+                for (int c8 = 0; c8 < CPT / 8; ++c8) { a[c8 * 4] = pk[c8].x; a[c8 * 4 + 1] = pk[c8].y; a[c8 * 4 + 2] = pk[c8].z; a[c8 * 4 + 3] = pk[c8].w; }
+                tc::tmem_st8(tlane + (uint32_t)s * 128u + c0, a);
+#pragma unroll
+                for (int c8 = 0; c8 < CPT / 8; ++c8) { a[c8 * 4] = dk[c8].x; a[c8 * 4 + 1] = dk[c8].y; a[c8 * 4 + 2] = dk[c8].z; a[c8 * 4 + 3] = dk[c8].w; }
+                tc::tmem_st8(tlane + (uint32_t)s * 128u + 64u + c0, a);
+            }
+            if (n >= 2) tc::mbar_wait(&bar_acc[s], (uint32_t)(((n >> 1) - 1) & 1));   // dQ of tile i-2 has read this dS^T buffer
             uint8_t* dst = ds0 + (i & 1) * DS_B + hq * 8 * (128 * 16);
 #pragma unroll
-            for (int c8 = 0; c8 < CPT / 8; ++c8) {
-                *reinterpret_cast<uint4*>(pt + c8 * (128 * 16)) = pk[c8];
-                *reinterpret_cast<uint4*>(dst + c8 * (128 * 16)) = dk[c8];
-            }
+            for (int c8 = 0; c8 < CPT / 8; ++c8) *reinterpret_cast<uint4*>(dst + c8 * (128 * 16)) = dk[c8];
+            tc::tmem_wait_st();
             tc::fence_async_smem();
             tc::fence_before_sync();
             __syncwarp();
@@ -1442,13 +1452,11 @@ static int attn_launch_bwd(const AttnWs& w, const float* lse, int64_t B, int64_t
     const DropCfg dc = make_drop(dropout_p, seed);
     const bool drop = dropout_p > 0.f;
     if (d == 32 && !(dbg & 128)) {                   // warp-specialised kernel (GAOT_ATTN_DEBUG bit 7 selects the older one)
-        const int ncw = (dbg & 256) ? 8 : 16;
 #define GAOT_BWD2_LAUNCH(NCW, DR)                                                                                      \
     do { GAOT_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<NCW, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bw2::SMEM)); \
          attn_bwd2_kernel<NCW, DR><<<grid, (NCW + 6) * 32, bw2::SMEM, st>>>(w.Qb, w.Kb, w.Vb, w.dOb, w.Dvec, w.dQacc, w.dKh, w.dVh, \
                                                                            (int)S, H, Hkv, scale, scale_dk, dc); } while (0)
-        if (ncw == 16) { if (drop) GAOT_BWD2_LAUNCH(16, true); else GAOT_BWD2_LAUNCH(16, false); }
-        else           { if (drop) GAOT_BWD2_LAUNCH(8, true);  else GAOT_BWD2_LAUNCH(8, false); }
+        if (drop) GAOT_BWD2_LAUNCH(16, true); else GAOT_BWD2_LAUNCH(16, false);
 #undef GAOT_BWD2_LAUNCH
         GAOT_LAUNCH_CHECK();
         return GAOT_OK;

@@ -115,14 +115,22 @@ rmsnorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, co
     }
 }
 
-// out[c] = sum_p part[p][c]   (fixed order)
+// out[c] = sum_p part[p][c]   (fixed order: 8 interleaved part lanes, then lanes 0..7).  CTA = 32 columns x 8 part lanes.
 __global__ void __launch_bounds__(256)
 colsum_reduce_kernel(const float* __restrict__ part, int nparts, int64_t N, float* __restrict__ out) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= N) return;
+    __shared__ float red[8][32];
+    const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+    const int64_t c = (int64_t)blockIdx.x * 32 + cl;
     float s = 0.f;
-    for (int p = 0; p < nparts; ++p) s += part[(size_t)p * N + c];
-    out[c] = s;
+    if (c < N)
+        for (int p = pl; p < nparts; p += 8) s += part[(size_t)p * N + c];
+    red[pl][cl] = s;
+    __syncthreads();
+    if (pl == 0 && c < N) {
+#pragma unroll
+        for (int k = 1; k < 8; ++k) s += red[k][cl];
+        out[c] = s;
+    }
 }
 
 // column sums of x [M,N] (bias gradients): CTA (256 threads = 64 float4 columns x 4 row lanes) over a row slab
@@ -243,7 +251,7 @@ int gaot_rmsnorm_backward(const float* dy, const float* x, const float* rstd, co
 #undef GAOT_RN
         GAOT_LAUNCH_CHECK();
     }
-    colsum_reduce_kernel<<<nblk(H, 256), 256, 0, st>>>(part, (int)grid, H, dw);
+    colsum_reduce_kernel<<<nblk(H, 32), 256, 0, st>>>(part, (int)grid, H, dw);
     GAOT_LAUNCH_CHECK();
     return GAOT_OK;
 }
@@ -259,7 +267,7 @@ int gaot_colsum(const float* x, int64_t M, int64_t N, float* out, void* ws, size
     dim3 grid(nblk(N, 256), (unsigned)slabs);
     colsum_part_kernel<<<grid, 256, 0, st>>>(x, M, N, rows_per, (float*)ws);
     GAOT_LAUNCH_CHECK();
-    colsum_reduce_kernel<<<nblk(N, 256), 256, 0, st>>>((const float*)ws, (int)slabs, N, out);
+    colsum_reduce_kernel<<<nblk(N, 32), 256, 0, st>>>((const float*)ws, (int)slabs, N, out);
     GAOT_LAUNCH_CHECK();
     return GAOT_OK;
 }
