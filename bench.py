@@ -123,6 +123,14 @@ def main():
     ap.add_argument("--shard", action="store_true", help="intra-sample sharding: all ranks cooperate on ONE sample (strong scaling)")
     ap.add_argument("--profile-step", action="store_true", help="warm up, then run ONE step between cudaProfilerStart/Stop (for ncu --profile-from-start off) and exit")
     args = ap.parse_args()
+    # the contract is ONE JSON line on stdout: libraries that print to the C-level stdout (NCCL prints its version line
+    # there) are sent to stderr; the JSON line goes to the saved descriptor
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -142,12 +150,12 @@ def main():
             return
         sec, cores, sample, parts = run_cpu_arm(wl, args.steps, min(args.warmup, 1), "reference")
         v = 1.0 / sec
-        print(json.dumps({"impl": "reference", "metric": "fwd+bwd samples/s", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+        emit({"impl": "reference", "metric": "fwd+bwd samples/s", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                           "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample,
                                            "parts_s": parts},
-                          "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                          "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
 
     # ------------------------------------------------------------------ our arm (B200)
@@ -307,7 +315,7 @@ def main():
                 out["cpu_baseline"] = {"value": 1.0 / sec, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample, "parts_s": parts}
             except Exception as e:  # the baseline is reporting only; never lose the GPU line
                 out["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port", "sample": f"failed: {e}"}
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
