@@ -44,6 +44,8 @@ _SIGS = {
     "gaot_gno_backward": (c_int, [P, c_int64, P, c_int64, P, c_int32, P, P, P, c_int64, POINTER(MlpDesc), P,
                                   c_int, c_int, c_int, P, P, c_size_t, P, P, P]),
     "gaot_geo_stats": (c_int, [P, c_int64, P, c_int64, P, P, P, P]),
+    "gaot_geo_moments": (c_int, [P, c_int64, P, c_int64, P, P, P, P]),
+    "gaot_geo_from_moments": (c_int, [P, c_int64, P, P]),
     "gaot_geo_zscore_workspace_bytes": (c_size_t, [c_int64]),
     "gaot_geo_zscore": (c_int, [P, c_int64, c_int32, P, c_size_t, P]),
     "gaot_attn_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32, c_int32, c_int32]),

@@ -20,20 +20,10 @@ __device__ __forceinline__ void jacobi_rot(double& app, double& aqq, double& apq
     arp = nrp; arq = nrq;
 }
 
-__global__ void __launch_bounds__(128)
-geo_stats_kernel(const float* __restrict__ src_pos, const float* __restrict__ qry_pos, int64_t nq,
-                 const int32_t* __restrict__ rowptr, const int32_t* __restrict__ csr_src,
-                 float* __restrict__ feat) {
-    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nq) return;
-    const int b = rowptr[q], e = rowptr[q + 1];
-    float* o = feat + q * 9;
-    if (e == b) {
-#pragma unroll
-        for (int i = 0; i < 9; ++i) o[i] = 0.f;
-        return;
-    }
-    const float qx = qry_pos[q * 3], qy = qry_pos[q * 3 + 1], qz = qry_pos[q * 3 + 2];
+// moments of (y - x) over one CSR row, centred on the query: m = {n, sum d, sum d^2, sum dx,dy,dz, sum xx,xy,xz,yy,yz,zz}.
+// Sums (not means), so the partials of several physical-point shards add up (sharded encoder).
+__device__ __forceinline__ void geo_row_moments(const float* __restrict__ src_pos, const int32_t* __restrict__ csr_src,
+                                                int b, int e, float qx, float qy, float qz, float (&m)[12]) {
     float sd = 0.f, sd2 = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
     float cxx = 0.f, cxy = 0.f, cxz = 0.f, cyy = 0.f, cyz = 0.f, czz = 0.f;
     for (int p = b; p < e; ++p) {
@@ -46,14 +36,26 @@ geo_stats_kernel(const float* __restrict__ src_pos, const float* __restrict__ qr
         sx += dx; sy += dy; sz += dz;
         cxx += dx * dx; cxy += dx * dy; cxz += dx * dz; cyy += dy * dy; cyz += dy * dz; czz += dz * dz;
     }
-    const float n = (float)(e - b), inv = 1.0f / n;
-    const float davg = sd * inv;
-    float dvar = sd2 * inv - davg * davg;
+    m[0] = (float)(e - b); m[1] = sd; m[2] = sd2; m[3] = sx; m[4] = sy; m[5] = sz;
+    m[6] = cxx; m[7] = cxy; m[8] = cxz; m[9] = cyy; m[10] = cyz; m[11] = czz;
+}
+
+// moments -> [N_i, D_avg, D_var, delta(3), eigenvalues(3) descending]; zero row for an empty query
+__device__ __forceinline__ void geo_finalize(const float (&m)[12], float* __restrict__ o) {
+    const float n = m[0];
+    if (n <= 0.f) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) o[i] = 0.f;
+        return;
+    }
+    const float inv = 1.0f / n;
+    const float davg = m[1] * inv;
+    float dvar = m[2] * inv - davg * davg;
     dvar = dvar > 0.f ? dvar : 0.f;
-    const double mx = (double)sx / n, my = (double)sy / n, mz = (double)sz / n;
-    double axx = (double)cxx / n - mx * mx + 1e-6, ayy = (double)cyy / n - my * my + 1e-6,
-           azz = (double)czz / n - mz * mz + 1e-6;
-    double axy = (double)cxy / n - mx * my, axz = (double)cxz / n - mx * mz, ayz = (double)cyz / n - my * mz;
+    const double mx = (double)m[3] / n, my = (double)m[4] / n, mz = (double)m[5] / n;
+    double axx = (double)m[6] / n - mx * mx + 1e-6, ayy = (double)m[9] / n - my * my + 1e-6,
+           azz = (double)m[11] / n - mz * mz + 1e-6;
+    double axy = (double)m[7] / n - mx * my, axz = (double)m[8] / n - mx * mz, ayz = (double)m[10] / n - my * mz;
 #pragma unroll 1
     for (int sweep = 0; sweep < 8; ++sweep) {
         jacobi_rot(axx, ayy, axy, axz, ayz);   // (p,q) = (x,y), r = z
@@ -68,6 +70,38 @@ geo_stats_kernel(const float* __restrict__ src_pos, const float* __restrict__ qr
     o[0] = n; o[1] = davg; o[2] = dvar;
     o[3] = (float)mx; o[4] = (float)my; o[5] = (float)mz;
     o[6] = (float)l0; o[7] = (float)l1; o[8] = (float)l2;
+}
+
+__global__ void __launch_bounds__(128)
+geo_stats_kernel(const float* __restrict__ src_pos, const float* __restrict__ qry_pos, int64_t nq,
+                 const int32_t* __restrict__ rowptr, const int32_t* __restrict__ csr_src,
+                 float* __restrict__ feat) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    float m[12];
+    geo_row_moments(src_pos, csr_src, rowptr[q], rowptr[q + 1], qry_pos[q * 3], qry_pos[q * 3 + 1], qry_pos[q * 3 + 2], m);
+    geo_finalize(m, feat + q * 9);
+}
+
+// the two halves as separate kernels: per-shard moment partials [nq,12] -> (all-reduce) -> features
+__global__ void __launch_bounds__(128)
+geo_moments_kernel(const float* __restrict__ src_pos, const float* __restrict__ qry_pos, int64_t nq,
+                   const int32_t* __restrict__ rowptr, const int32_t* __restrict__ csr_src, float* __restrict__ mom) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    float m[12];
+    geo_row_moments(src_pos, csr_src, rowptr[q], rowptr[q + 1], qry_pos[q * 3], qry_pos[q * 3 + 1], qry_pos[q * 3 + 2], m);
+    float4* o = reinterpret_cast<float4*>(mom + q * 12);
+    o[0] = make_float4(m[0], m[1], m[2], m[3]); o[1] = make_float4(m[4], m[5], m[6], m[7]); o[2] = make_float4(m[8], m[9], m[10], m[11]);
+}
+__global__ void __launch_bounds__(128)
+geo_from_moments_kernel(const float* __restrict__ mom, int64_t nq, float* __restrict__ feat) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const float4* i = reinterpret_cast<const float4*>(mom + q * 12);
+    const float4 a = i[0], b = i[1], c = i[2];
+    const float m[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+    geo_finalize(m, feat + q * 9);
 }
 
 // ---- global z-score: per-feature mean and unbiased std over all queries (fp64 accumulation) ----
@@ -128,6 +162,24 @@ int gaot_geo_stats(const float* src_pos, int64_t n_src, const float* qry_pos, in
     GAOT_CHECK_ARG(nq >= 0 && feat != nullptr, "geo_stats: bad arguments");
     if (nq == 0) return GAOT_OK;
     geo_stats_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, (cudaStream_t)stream>>>(src_pos, qry_pos, nq, rowptr, csr_src, feat);
+    GAOT_LAUNCH_CHECK();
+    return GAOT_OK;
+}
+
+int gaot_geo_moments(const float* src_pos, int64_t n_src, const float* qry_pos, int64_t nq,
+                     const int32_t* rowptr, const int32_t* csr_src, float* moments, void* stream) {
+    (void)n_src;
+    GAOT_CHECK_ARG(nq >= 0 && moments != nullptr, "geo_moments: bad arguments");
+    if (nq == 0) return GAOT_OK;
+    geo_moments_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, (cudaStream_t)stream>>>(src_pos, qry_pos, nq, rowptr, csr_src, moments);
+    GAOT_LAUNCH_CHECK();
+    return GAOT_OK;
+}
+
+int gaot_geo_from_moments(const float* moments, int64_t nq, float* feat, void* stream) {
+    GAOT_CHECK_ARG(nq >= 0 && moments != nullptr && feat != nullptr, "geo_from_moments: bad arguments");
+    if (nq == 0) return GAOT_OK;
+    geo_from_moments_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, (cudaStream_t)stream>>>(moments, nq, feat);
     GAOT_LAUNCH_CHECK();
     return GAOT_OK;
 }

@@ -1,4 +1,5 @@
 // gno.cu -- C ABI of the fused GNO (IntegralTransform) forward / backward.
+#include <cstdlib>
 #include "gno_common.cuh"
 
 namespace gaot {
@@ -12,7 +13,19 @@ bool gno_backward_bf16_supported(const GnoArgs& a);
 bool gno_forward_bf16_supported(const GnoArgs& a);
 int gno_backward_bf16(const GnoArgs& a, const float* d_out, void* ws, size_t ws_bytes, float* d_params, float* d_f,
                       cudaStream_t st);
+// second-generation tensor-core kernels (gno_tc2.cu)
+bool gno_forward_tc2_supported(const GnoArgs& a);
+int gno_forward_tc2(const GnoArgs& a, void* ws, size_t ws_bytes, float* out, cudaStream_t st);
+bool gno_backward_tc2_supported(const GnoArgs& a);
+int gno_backward_tc2(const GnoArgs& a, const float* d_out, void* ws, size_t ws_bytes, float* d_params, float* d_f,
+                     cudaStream_t st);
 }  // namespace gaot
+
+// GAOT_GNO_GEN=1 pins the first-generation tensor-core kernels (A/B timing on the GPU box); default: newest that fits
+static bool use_gen2() {
+    const char* e = getenv("GAOT_GNO_GEN");
+    return !(e && e[0] == '1');
+}
 
 using namespace gaot;
 
@@ -59,6 +72,7 @@ int gaot_gno_forward(const float* y_pos, int64_t n_src, const float* x_pos, int6
     if (rc) return rc;
     if (precision == 0) return gno_forward_fp32(a, ws, ws_bytes, out, (cudaStream_t)stream);
     if (precision == 1) {
+        if (use_gen2() && gno_forward_tc2_supported(a)) return gno_forward_tc2(a, ws, ws_bytes, out, (cudaStream_t)stream);
         if (gno_forward_bf16_supported(a)) return gno_forward_bf16(a, ws, ws_bytes, out, (cudaStream_t)stream);
         return gno_forward_fp32(a, ws, ws_bytes, out, (cudaStream_t)stream);     // outside the tcgen05 envelope: FP32 kernel
     }
@@ -76,6 +90,8 @@ int gaot_gno_backward(const float* y_pos, int64_t n_src, const float* x_pos, int
     if (rc) return rc;
     GAOT_CHECK_ARG(d_out != nullptr && d_params != nullptr, "gno_backward: null gradient buffers");
     // precision 1: tensor-core backward when the MLP fits its envelope, otherwise the FP32 recompute
+    if (precision == 1 && use_gen2() && gno_backward_tc2_supported(a))
+        return gno_backward_tc2(a, d_out, ws, ws_bytes, d_params, d_f_y, (cudaStream_t)stream);
     if (precision == 1 && gno_backward_bf16_supported(a))
         return gno_backward_bf16(a, d_out, ws, ws_bytes, d_params, d_f_y, (cudaStream_t)stream);
     return gno_backward_fp32(a, d_out, ws, ws_bytes, d_params, d_f_y, (cudaStream_t)stream);

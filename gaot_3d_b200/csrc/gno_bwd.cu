@@ -364,7 +364,7 @@ int gno_bwd_reduce(const float* partial, int nparts, int n_params, float* d_para
     return GAOT_OK;
 }
 
-size_t gno_backward_ws_bytes(int n_params) { return align_up((size_t)kNumSMs * n_params * sizeof(float)) + 256; }
+size_t gno_backward_ws_bytes(int n_params) { return align_up((size_t)2 * kNumSMs * n_params * sizeof(float)) + 256; }   // <= 2 CTAs per SM
 
 int gno_backward_fp32(const GnoArgs& a_in, const float* d_out, void* ws, size_t ws_bytes,
                       float* d_params, float* d_f, cudaStream_t st) {

@@ -144,6 +144,13 @@ int gaot_gno_backward(const float* y_pos, int64_t n_src, const float* x_pos, int
  */
 int gaot_geo_stats(const float* src_pos, int64_t n_src, const float* qry_pos, int64_t nq,
                    const int32_t* rowptr, const int32_t* csr_src, float* feat, void* stream);
+/* The two halves of gaot_geo_stats for a query set whose sources are sharded over ranks (intra-sample sharding,
+ * no reference counterpart; the statistics are those of geoembed.py:126-162): per-query moment SUMS
+ * moments[nq,12] = {n, sum d, sum d^2, sum (y-x) (3), sum (y-x)(y-x)^T upper triangle (6)} centred on the
+ * query, which add across shards (all-reduce), then moments -> the same [nq,9] features. */
+int gaot_geo_moments(const float* src_pos, int64_t n_src, const float* qry_pos, int64_t nq,
+                     const int32_t* rowptr, const int32_t* csr_src, float* moments, void* stream);
+int gaot_geo_from_moments(const float* moments, int64_t nq, float* feat, void* stream);
 size_t gaot_geo_zscore_workspace_bytes(int64_t nq);
 int gaot_geo_zscore(float* feat, int64_t nq, int32_t nfeat, void* ws, size_t ws_bytes, void* stream);
 

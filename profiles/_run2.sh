@@ -1,0 +1,6 @@
+set -x
+mkdir -p gpurun_out
+for k in gno_fwd_tc2_kernelILi3 gno_bwd_tc2_kernelILi3 gno_bwd_tc2_kernelILi4; do
+  timeout 300 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:$k --launch-skip 2 -c 1 -f -o gpurun_out/prof_$k python tests/prof_ops.py gno 2 > gpurun_out/p_$k.log 2>&1
+done
+ls -la gpurun_out
