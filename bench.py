@@ -26,6 +26,9 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     "drivaernet500k": dict(n_points=500_000, latent=(64, 64, 32), box="drivaernet", k=1, layers=10, hidden=256, heads=8, ffn=1024),
+    # BASELINE configs[2]: NASA-CRM-shaped sample, bidirectional knn+radius graph, geometric embedding in the encoder only
+    "crm500k": dict(n_points=500_000, latent=(64, 64, 32), box="crm", k=1, layers=10, hidden=256, heads=8, ffn=1024,
+                    strategy="bidirectional", radius=0.033, geoembed=[True, False], features="mach_aoa"),
     "small": dict(n_points=32_768, latent=(16, 16, 16), box="drivaernet", k=1, layers=4, hidden=256, heads=8, ffn=1024),
     # BASELINE configs[3]: DrivaerML-shaped full-resolution sample; with --shard the physical points of ONE
     # sample are split across the ranks (encoder partial sums all-reduced, decoder query-sharded)
@@ -46,7 +49,7 @@ def peaks():
 def make_sample(wl, seed):
     from tests import synth
     pos = synth.surface_cloud(wl["n_points"], wl["box"], seed=seed)
-    nrm = synth.unit_normals(wl["n_points"], seed=seed)
+    nrm = synth.mach_aoa(wl["n_points"], seed=seed) if wl.get("features") == "mach_aoa" else synth.unit_normals(wl["n_points"], seed=seed)
     rng = np.random.default_rng(seed + 7)
     tgt = rng.standard_normal((wl["n_points"], C_OUT)).astype(np.float32)
     return pos, nrm, tgt
@@ -120,6 +123,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gno-precision", default="bf16", choices=["fp32", "bf16"],
                     help="per-edge kernel MLP operands: bf16 tcgen05 (rtol 2e-2 tier of the north star, default) or fp32 CUDA cores (rtol 1e-5 tier)")
+    ap.add_argument("--node-mlp", default="tf32", choices=["fp32", "tf32"],
+                    help="node-level torch GEMMs (lifting / projection / recovery): TF32 tensor cores (what the reference's default Conv1d node MLPs get from cuDNN) or strict fp32")
     ap.add_argument("--shard", action="store_true", help="intra-sample sharding: all ranks cooperate on ONE sample (strong scaling)")
     ap.add_argument("--profile-step", action="store_true", help="warm up, then run ONE step between cudaProfilerStart/Stop (for ncu --profile-from-start off) and exit")
     args = ap.parse_args()
@@ -137,8 +142,14 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     S = (wl["latent"][0] // PATCH) * (wl["latent"][1] // PATCH) * (wl["latent"][2] // PATCH)
-    config = {"workload": f"DrivAerNet++-shaped {wl['n_points']}-point surface cloud, latent {wl['latent']}, knn k={wl['k']} enc+dec, "
-                          f"C={C_LIFT}, in 6 (pos+normals), out 4 (pressure+WSS), {wl['layers']}-layer transformer H={wl['hidden']} S={S}, "
+    strat = wl.get("strategy", "knn")
+    strat_txt = (f"{strat[0]} encoder / {strat[1]} decoder" if isinstance(strat, (list, tuple)) else f"{strat} enc+dec") + \
+                (f" (k={wl['k']}, r={wl.get('radius', 0.033)})" if strat != "knn" else f" k={wl['k']}")
+    shape = {"drivaernet": "DrivAerNet++", "drivaerml": "DrivaerML", "crm": "NASA-CRM"}[wl["box"]]
+    c_in = 5 if wl.get("features") == "mach_aoa" else C_IN
+    config = {"workload": f"{shape}-shaped {wl['n_points']}-point surface cloud, latent {wl['latent']}, {strat_txt}, "
+                          f"C={C_LIFT}, in {c_in} ({'pos+Mach/AOA' if c_in == 5 else 'pos+normals'}), out 4 (pressure+WSS), "
+                          f"geoembed {wl.get('geoembed', [False, False])}, {wl['layers']}-layer transformer H={wl['hidden']} S={S}, "
                           f"fwd+bwd+AdamW, online graph build, batch 1/GPU, atten_dropout 0",
               "n_points": wl["n_points"], "latent_tokens": list(wl["latent"]), "seq_len": S,
               "parallelism": (f"shard{world} (one sample split across ranks)" if args.shard else f"dp{world}") if world > 1 else "single",
@@ -172,16 +183,17 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     G.set_gno_precision(args.gno_precision)
+    G.set_node_mlp_tf32(args.node_mlp == "tf32")
     torch.manual_seed(0)
     mc = G.MAGNOConfig(gno_coord_dim=3, lifting_channels=C_LIFT, neighbor_strategy=wl.get("strategy", "knn"), k_neighbors=wl["k"],
                        gno_radius=wl.get("radius", 0.033),
-                       mlp_type="linear", precompute_edges=False, use_geoembed=[False, False], encoder_feature_attr=["pos", "c"],
+                       mlp_type="linear", precompute_edges=False, use_geoembed=wl.get("geoembed", [False, False]), encoder_feature_attr=["pos", "c"],
                        in_gno_channel_mlp_hidden_layers=[64, 64, 64], out_gno_channel_mlp_hidden_layers=[64, 64], projection_channels=256)
     tc = G.TransformerConfig(patch_size=PATCH, hidden_size=wl["hidden"], num_layers=wl["layers"], positional_embedding="rope")
     tc.attn_config.hidden_size, tc.attn_config.num_heads, tc.attn_config.num_kv_heads = wl["hidden"], wl["heads"], wl["heads"]
     tc.attn_config.atten_dropout = 0.0
     tc.ffn_config.hidden_size = wl["ffn"]
-    model = G.GAOT3D(C_IN, C_OUT, mc, tc, latent_tokens=wl["latent"]).to(dev).train()
+    model = G.GAOT3D(c_in, C_OUT, mc, tc, latent_tokens=wl["latent"]).to(dev).train()
     if world > 1 and not args.shard:
         model_step = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank])
     else:
@@ -303,7 +315,7 @@ def main():
            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if args.shard else "weak", "vs_baseline": None,
            "dtype": ("bf16 tensor-core operands / f32 accumulate (attention, transformer dense layers" +
                      (", GNO edge MLP)" if args.gno_precision == "bf16" else "); f32 GNO edge MLP") +
-                     "; f32 residual stream, statistics, node MLPs, optimizer"), "data": "synthetic",
+                     f"; f32 residual stream, statistics, optimizer; node MLPs {args.node_mlp}"), "data": "synthetic",
            "config": config, "clocks": clk,
            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                    "ms_per_step": ms_e2e / args.steps},

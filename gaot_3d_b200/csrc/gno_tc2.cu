@@ -76,35 +76,37 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn_maj
 // forward
 // =====================================================================================================
 struct Tc2Layout {
-    int w_off[GNO_MAX_LAYERS];     // byte offsets of the f16 weight tiles
-    int kpad[GNO_MAX_LAYERS];
-    int bh_off[GNO_MAX_LAYERS];    // half offsets (from bias_h) of the hidden-layer biases
-    int bias_h, bias_last;         // byte offsets: f16 hidden biases, fp32 last-layer bias
-    int grp_base, grp_stride;      // per-stream regions: [A0 4K | ACT 16K | F 18K | ints]
+    int w_off[GNO_MAX_LAYERS];     // byte offsets of the f16 weight tiles [N x kpad]: [W (x 1/2 for l >= 1) | bias | 0]
+    int kpad[GNO_MAX_LAYERS];      // 16 for layer 0 (12 coordinate halves + ones column), K + 16 otherwise (ones chunk + zero chunk)
+    int grp_base, grp_stride;      // per-stream regions
     int total_bytes;
 };
-constexpr int G_A0 = 0, G_ACT = 4096, G_F = 4096 + 16384, G_INTS = 4096 + 16384 + T2E * FROW * 4;
-constexpr int G_STRIDE = 41984;
-static_assert(G_INTS + (5 * T2E + 16) * 4 <= G_STRIDE, "per-stream region too small");
+// per-stream region: [A0 4K | ACT 20K = 64 activation columns + ones chunk + zero chunk | F 18K | per-row ints x2 | segment table]
+constexpr int G_A0 = 0, G_ACT = 4096, G_F = G_ACT + 20480, G_INTS = G_F + T2E * FROW * 4;
+constexpr int G_ROWINTS = 3 * T2E;                       // s_qry, s_rb, s_re of one buffer
+constexpr int G_STRIDE = 47104;
+static_assert(G_INTS + (2 * G_ROWINTS + T2E + 4 + 8) * 4 <= G_STRIDE, "per-stream region too small");
 
 static Tc2Layout tc2_layout(const GnoArgs& a) {
     Tc2Layout L;
     memset(&L, 0, sizeof(L));
     int off = 0;
     for (int l = 0; l < a.n_layers; ++l) {
-        L.kpad[l] = (l == 0) ? 16 : a.dims[l];
+        L.kpad[l] = (l == 0) ? 16 : a.dims[l] + 16;
         L.w_off[l] = off; off += a.dims[l + 1] * L.kpad[l] * 2;
     }
-    off = (off + 127) / 128 * 128;
-    L.bias_h = off;
-    int bo = 0;
-    for (int l = 0; l + 1 < a.n_layers; ++l) { L.bh_off[l] = bo; bo += a.dims[l + 1]; }
-    off += (bo * 2 + 127) / 128 * 128;
-    L.bias_last = off; off += 256;
     off = (off + 1023) / 1024 * 1024;
     L.grp_base = off; L.grp_stride = G_STRIDE;
     L.total_bytes = off + F2G * G_STRIDE;
     return L;
+}
+
+// 2 * gelu(x) on a packed pair: x + x * tanh(...).  The factor 1/2 lives in the next layer's weights (exact: power of two).
+__device__ __forceinline__ __half2 gelu2x_h2(__half2 x) {
+    const __half2 c1 = __float2half2_rn(0.0356774081f), c0 = __float2half2_rn(0.7978845608f);
+    const __half2 x2 = __hmul2(x, x);
+    const __half2 u = __hmul2(x, __hfma2(x2, c1, c0));
+    return __hfma2(x, tanh_h2(u), x);
 }
 
 template <int NL>
@@ -116,7 +118,8 @@ gno_fwd_tc2_kernel(const GnoArgs a, const Tc2Layout L, float* __restrict__ out, 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = tid >> 7, row = tid & 127, wg = warp & 3;
 
-    // ---- weights -> f16 chunk-major K-major B tiles; hidden biases -> f16, last bias -> fp32 ----
+    // ---- weights -> f16 chunk-major K-major B tiles.  Layers >= 1 carry the 1/2 of the GELU; the bias of every
+    //      layer is one more K column that meets a constant 1 in the A operand (no bias add in the epilogues) ----
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
         const int K = a.dims[l], N = a.dims[l + 1], KP = L.kpad[l];
@@ -125,21 +128,19 @@ gno_fwd_tc2_kernel(const GnoArgs a, const Tc2Layout L, float* __restrict__ out, 
         for (int idx = tid; idx < N * KP; idx += F2T) {
             const int n = idx / KP, k = idx - n * KP;
             float v;
-            if (l == 0) v = k < 12 ? W[n * K + (k % 6)] : 0.f;        // [hi(6) | lo(6) | 0 0 0 0] see the same weights
-            else v = W[n * K + k];
+            if (l == 0) v = k < 12 ? W[n * K + (k % 6)] : (k == 12 ? a.params[a.b_off[0] + n] : 0.f);   // [hi(6) | lo(6) | bias | 0 0 0]
+            else v = k < K ? 0.5f * W[n * K + k] : (k == K ? a.params[a.b_off[l] + n] : 0.f);
             *reinterpret_cast<__half*>(Ws + tc::cm_off(N, n, k)) = __float2half_rn(v);
         }
-        if (l < NL - 1) {
-            __half* bh = reinterpret_cast<__half*>(sm + L.bias_h) + L.bh_off[l];
-            for (int j = tid; j < N; j += F2T) bh[j] = __float2half_rn(a.params[a.b_off[l] + j]);
-        } else {
-            float* bl = reinterpret_cast<float*>(sm + L.bias_last);
-            for (int j = tid; j < N; j += F2T) bl[j] = a.params[a.b_off[l] + j];
-        }
+    }
+    if (row < T2E) {                               // constant ones / zero chunks behind the 64 activation columns
+        uint8_t* act = sm + L.grp_base + g * L.grp_stride + G_ACT;
+        *reinterpret_cast<uint4*>(act + 8 * (128 * 16) + row * 16) = make_uint4(0x00003C00u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(act + 9 * (128 * 16) + row * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, 64 * F2G);
     if (tid == 0) {
-        for (int i = 0; i < F2G; ++i) { tc::mbar_init(&mbar_mma[i], 1); tc::mbar_init(&mbar_f[i], 1); }
+        for (int i = 0; i < F2G; ++i) { tc::mbar_init(&mbar_mma[i], 1); tc::mbar_init(&mbar_f[i], 128); }
         tc::mbar_fence_init();
     }
     tc::fence_async_smem();
@@ -154,12 +155,9 @@ gno_fwd_tc2_kernel(const GnoArgs a, const Tc2Layout L, float* __restrict__ out, 
     uint8_t* A0 = G0 + G_A0;
     uint8_t* ACT = G0 + G_ACT;
     float* F = reinterpret_cast<float*>(G0 + G_F);
-    int* s_qry = reinterpret_cast<int*>(G0 + G_INTS);
-    int* s_rb = s_qry + T2E;
-    int* s_re = s_rb + T2E;
-    int* seg_first = s_re + T2E;               // [T2E + 1]
-    int* s_misc = seg_first + T2E + 4;         // [8]
-    const float* bias_last = reinterpret_cast<const float*>(sm + L.bias_last);
+    int* rowints = reinterpret_cast<int*>(G0 + G_INTS);          // [2][s_qry | s_rb | s_re]
+    int* seg_first = rowints + 2 * G_ROWINTS;                    // [T2E + 1]
+    int* s_misc = seg_first + T2E + 4;                           // [8]
 
     const bool has_f = a.f_y != nullptr;
     const tc::Desc dA0 = tc::kmajor(tc::smem_u32(A0), 128);
@@ -183,42 +181,63 @@ gno_fwd_tc2_kernel(const GnoArgs a, const Tc2Layout L, float* __restrict__ out, 
             __syncwarp();
         }
     };
+    // layer-0 operand row [y hi | x hi | y lo | x lo | 1 | 0] in f16 + the per-row ints of tile buffer `buf`
+    auto write_row = [&](int buf, const float (&c6)[6], int qry, int rb, int re) {
+        __half hi[6], lo[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            hi[j] = __float2half_rn(c6[j]);
+            lo[j] = __float2half_rn(c6[j] - __half2float(hi[j]));
+        }
+        uint4 c0, c1;
+        c0.x = h2_as_u32(__halves2half2(hi[0], hi[1])); c0.y = h2_as_u32(__halves2half2(hi[2], hi[3]));
+        c0.z = h2_as_u32(__halves2half2(hi[4], hi[5])); c0.w = h2_as_u32(__halves2half2(lo[0], lo[1]));
+        c1.x = h2_as_u32(__halves2half2(lo[2], lo[3])); c1.y = h2_as_u32(__halves2half2(lo[4], lo[5])); c1.z = 0x00003C00u; c1.w = 0u;
+        *reinterpret_cast<uint4*>(A0 + row * 16) = c0;
+        *reinterpret_cast<uint4*>(A0 + 128 * 16 + row * 16) = c1;
+        int* ri = rowints + buf * G_ROWINTS;
+        ri[row] = qry; ri[T2E + row] = rb; ri[2 * T2E + row] = re;
+    };
 
-    for (int tile = blockIdx.x * F2G + g; tile < a.ntiles; tile += gridDim.x * F2G) {
+    const int tstep = gridDim.x * F2G;
+    int tile = blockIdx.x * F2G + g;
+    // ---- software pipeline: indices of tile k+1 are loaded during layer 0 of tile k, its coordinates during
+    //      layer 1, its layer-0 operand is written before the last layer -> no dependent global latency per tile ----
+    int src = 0, qry = -1, qprev = -2;
+    if (tile < a.ntiles) {
+        const int e0 = tile * T2E;
+        const bool valid = row < min(T2E, a.E - e0);
+        if (valid) { src = a.csr_src[e0 + row]; qry = a.csr_qry[e0 + row]; }
+        if (valid && row > 0) qprev = a.csr_qry[e0 + row - 1];
+        float c6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int rb = 0, re = 0;
+        if (valid) {
+            const float* py = a.y_pos + (size_t)src * 3;
+            const float* px = a.x_pos + (size_t)qry * 3;
+            c6[0] = py[0]; c6[1] = py[1]; c6[2] = py[2]; c6[3] = px[0]; c6[4] = px[1]; c6[5] = px[2];
+            rb = a.rowptr[qry]; re = a.rowptr[qry + 1];
+        }
+        write_row(0, c6, qry, rb, re);
+    }
+
+    for (int it = 0; tile < a.ntiles; tile += tstep, ++it) {
+        const int buf = it & 1;
         const int e0 = tile * T2E;
         const int ne = min(T2E, a.E - e0);
         const bool valid = row < ne;
-        const int src = valid ? a.csr_src[e0 + row] : 0;
-        const int qry = valid ? a.csr_qry[e0 + row] : -1;
-        const int qprev = (valid && row > 0) ? a.csr_qry[e0 + row - 1] : -2;
-        // ---- feature row -> padded staging tile by the bulk-copy engine ----
+        const int* s_qry = rowints + buf * G_ROWINTS;
+        const int* s_rb = s_qry + T2E;
+        const int* s_re = s_rb + T2E;
+        // ---- feature rows -> padded staging tile: 8 lanes per 128-byte row, 4 rows per warp instruction ----
         if (has_f) {
-            if (row == 0) tc::mbar_arrive_expect_tx(&mbar_f[g], (uint32_t)ne * Cout * 4);
-            if (valid) tc::bulk_copy_g2s(tc::smem_u32(F + row * FROW), a.f_y + (size_t)src * Cout, Cout * 4, &mbar_f[g]);
-        }
-        // ---- layer-0 operand: [y hi | x hi | y lo | x lo | 0] in f16 ----
-        {
-            float c6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            int rb = 0, re = 0;
-            if (valid) {
-                const float* py = a.y_pos + (size_t)src * 3;
-                const float* px = a.x_pos + (size_t)qry * 3;
-                c6[0] = py[0]; c6[1] = py[1]; c6[2] = py[2]; c6[3] = px[0]; c6[4] = px[1]; c6[5] = px[2];
-                rb = a.rowptr[qry]; re = a.rowptr[qry + 1];
-            }
-            __half hi[6], lo[6];
+            const uint32_t fbase = tc::smem_u32(F) + (uint32_t)(wg * 32) * (FROW * 4) + (lane & 7) * 16;
 #pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                hi[j] = __float2half_rn(c6[j]);
-                lo[j] = __float2half_rn(c6[j] - __half2float(hi[j]));
+            for (int j = 0; j < 8; ++j) {
+                const int r = j * 4 + (lane >> 3);
+                const int sr = __shfl_sync(0xffffffffu, src, r);
+                tc::cp_async16(fbase + (uint32_t)r * (FROW * 4), a.f_y + (size_t)sr * Cout + (lane & 7) * 4, wg * 32 + r < ne);
             }
-            uint4 c0, c1;
-            c0.x = h2_as_u32(__halves2half2(hi[0], hi[1])); c0.y = h2_as_u32(__halves2half2(hi[2], hi[3]));
-            c0.z = h2_as_u32(__halves2half2(hi[4], hi[5])); c0.w = h2_as_u32(__halves2half2(lo[0], lo[1]));
-            c1.x = h2_as_u32(__halves2half2(lo[2], lo[3])); c1.y = h2_as_u32(__halves2half2(lo[4], lo[5])); c1.z = 0u; c1.w = 0u;
-            *reinterpret_cast<uint4*>(A0 + row * 16) = c0;
-            *reinterpret_cast<uint4*>(A0 + 128 * 16 + row * 16) = c1;
-            s_qry[row] = qry; s_rb[row] = rb; s_re[row] = re;
+            tc::cp_async_mbar_arrive_noinc(&mbar_f[g]);
         }
         const bool head = valid && (row == 0 || qprev != qry);
         const unsigned bm = __ballot_sync(0xffffffffu, head);
@@ -238,9 +257,19 @@ gno_fwd_tc2_kernel(const GnoArgs a, const Tc2Layout L, float* __restrict__ out, 
                 seg_first[nseg] = ne;
             }
         }
+        // pipeline step A: indices of the next tile
+        const int ntile = tile + tstep;
+        const bool nvalid = ntile < a.ntiles && row < min(T2E, a.E - ntile * T2E);
+        int nsrc = 0, nqry = -1, nprev = -2;
+        if (nvalid) { nsrc = a.csr_src[ntile * T2E + row]; nqry = a.csr_qry[ntile * T2E + row]; }
+        if (nvalid && row > 0) nprev = a.csr_qry[ntile * T2E + row - 1];
+        float nc6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int nrb = 0, nre = 0;
 
 #pragma unroll
         for (int l = 0; l < NL; ++l) {
+            // pipeline step C (the layer-0 MMA of this tile has long read A0)
+            if (l == NL - 1 && ntile < a.ntiles) write_row(buf ^ 1, nc6, nqry, nrb, nre);
             tc::mbar_wait(&mbar_mma[g], ph_mma); ph_mma ^= 1;
             tc::fence_after_sync();
             if (l < NL - 1) {
@@ -249,19 +278,15 @@ gno_fwd_tc2_kernel(const GnoArgs a, const Tc2Layout L, float* __restrict__ out, 
                 tc::tmem_ld32_nowait(tlane, v0);
                 tc::tmem_ld32_nowait(tlane + 32, v1);
                 tc::tmem_wait_ld();
-                const uint4* bh4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(sm + L.bias_h) + L.bh_off[l]);
 #pragma unroll
                 for (int c8 = 0; c8 < 8; ++c8) {
-                    const uint4 bb = bh4[c8];
-                    const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
                     uint32_t o[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int c = (c8 & 3) * 8 + 2 * j;
                         const float lo_ = __uint_as_float(c8 < 4 ? v0[c] : v1[c]);
                         const float hi_ = __uint_as_float(c8 < 4 ? v0[c + 1] : v1[c + 1]);
-                        const __half2 z = __hadd2(__floats2half2_rn(lo_, hi_), u32_as_h2(bw[j]));
-                        o[j] = h2_as_u32(gelu_h2(z));
+                        o[j] = h2_as_u32(gelu2x_h2(__floats2half2_rn(lo_, hi_)));
                     }
                     *reinterpret_cast<uint4*>(ACT + c8 * (128 * 16) + row * 16) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
@@ -269,43 +294,56 @@ gno_fwd_tc2_kernel(const GnoArgs a, const Tc2Layout L, float* __restrict__ out, 
                 tc::fence_before_sync();
                 group_bar(g);
                 issue_layer(l + 1);
+                if (l == 0 && nvalid) {                                                           // pipeline step B
+                    const float* py = a.y_pos + (size_t)nsrc * 3;
+                    const float* px = a.x_pos + (size_t)nqry * 3;
+                    nc6[0] = py[0]; nc6[1] = py[1]; nc6[2] = py[2]; nc6[3] = px[0]; nc6[4] = px[1]; nc6[5] = px[2];
+                    nrb = a.rowptr[nqry]; nre = a.rowptr[nqry + 1];
+                }
             } else {
-                // last layer: bias, (* f_y[src]) in fp32, written in place over the staged feature row
+                // last layer: (* f_y[src]) in fp32, written in place over the staged feature row
                 float v[32];
                 tc::tmem_ld32(tlane, v);
                 if (has_f) { tc::mbar_wait(&mbar_f[g], ph_f); ph_f ^= 1; }
                 float* fr = F + row * FROW;
 #pragma unroll
                 for (int c = 0; c < 32; c += 4) {
-                    const float4 b = *reinterpret_cast<const float4*>(bias_last + c);
-                    float4 o = make_float4(v[c] + b.x, v[c + 1] + b.y, v[c + 2] + b.z, v[c + 3] + b.w);
+                    float4 o = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
                     if (has_f) {
                         const float4 f = *reinterpret_cast<const float4*>(fr + c);
                         o.x *= f.x; o.y *= f.y; o.z *= f.z; o.w *= f.w;
                     }
-                    if (valid) *reinterpret_cast<float4*>(fr + c) = o;
+                    *reinterpret_cast<float4*>(fr + c) = o;
                 }
                 tc::fence_before_sync();
                 group_bar(g);
+                // segmented sums: 8 threads (one float4 of channels each) per segment, 16 segments at a time
                 const int nseg = s_misc[4];
-                for (int s = wg; s < nseg; s += 4) {
+                const int quad = row & 7;
+                const float4* F4 = reinterpret_cast<const float4*>(F);
+                for (int s = row >> 3; s < nseg; s += 16) {
                     const int first = seg_first[s], lastE = seg_first[s + 1];
                     const int q = s_qry[first];
                     const int rb = s_rb[first], re = s_re[first];
-                    const bool starts_here = rb >= e0;
-                    const bool ends_here = re <= e0 + ne;
-                    float sum = 0.f;
-                    for (int e = first; e < lastE; ++e) sum += F[e * FROW + lane];
-                    if (starts_here) {
-                        if (ends_here && a.reduce == 0) sum = sum / (float)(re - rb);
-                        out[(size_t)q * Cout + lane] = sum;
+                    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int e = first; e < lastE; ++e) {
+                        const float4 t = F4[e * (FROW / 4) + quad];
+                        sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
+                    }
+                    if (rb >= e0) {                                          // segment starts in this tile
+                        if (re <= e0 + ne && a.reduce == 0) {
+                            const float inv = 1.0f / (float)(re - rb);
+                            sum.x *= inv; sum.y *= inv; sum.z *= inv; sum.w *= inv;
+                        }
+                        *reinterpret_cast<float4*>(out + (size_t)q * Cout + quad * 4) = sum;
                     } else {
-                        head_partial[(size_t)tile * Cout + lane] = sum;
+                        *reinterpret_cast<float4*>(head_partial + (size_t)tile * Cout + quad * 4) = sum;
                     }
                 }
             }
         }
-        tc::fence_async_smem();        // generic reads/writes of F and A0 before the next tile's async-proxy writes
+        src = nsrc; qry = nqry; qprev = nprev;
+        tc::fence_async_smem();        // generic accesses of F / A0 before the next tile's copies and MMA reads
         group_bar(g);
     }
     tc::fence_before_sync();
@@ -356,9 +394,9 @@ int gno_forward_tc2(const GnoArgs& a, void* ws, size_t ws_bytes, float* out, cud
 constexpr int B2T = 256;
 
 struct Tc2BwdLayout {
-    int w_off[GNO_MAX_LAYERS], b_off[GNO_MAX_LAYERS], kpad[GNO_MAX_LAYERS], h_off[GNO_MAX_LAYERS], gp_off[GNO_MAX_LAYERS];
+    int w_off[GNO_MAX_LAYERS], kpad[GNO_MAX_LAYERS], h_off[GNO_MAX_LAYERS], gp_off[GNO_MAX_LAYERS];
     int tm_dw[GNO_MAX_LAYERS];
-    int bias_base, a0, dz, total_bytes, tmem_cols;
+    int a0, dz, total_bytes, tmem_cols;
 };
 
 static Tc2BwdLayout tc2_bwd_layout(const GnoArgs& a) {
@@ -366,14 +404,9 @@ static Tc2BwdLayout tc2_bwd_layout(const GnoArgs& a) {
     memset(&L, 0, sizeof(L));
     int off = 0;
     for (int l = 0; l < a.n_layers; ++l) {
-        L.kpad[l] = (l == 0) ? 16 : a.dims[l];
+        L.kpad[l] = (l == 0) ? 16 : a.dims[l] + 16;           // [W | bias | 0]: the bias meets the ones column / chunk of the A operand
         L.w_off[l] = off; off += a.dims[l + 1] * L.kpad[l] * 2;
     }
-    off = (off + 1023) / 1024 * 1024;
-    L.bias_base = off;
-    int bo = 0;
-    for (int l = 0; l < a.n_layers; ++l) { L.b_off[l] = bo; bo += a.dims[l + 1]; }
-    off += (bo * 4 + 127) / 128 * 128;
     off = (off + 1023) / 1024 * 1024;
     L.a0 = off; off += T2E * 16 * 2;
     // dZ tile (single buffer).  An M = 128 read of it (dW GEMM, channels padded to 128) touches the 16 KB behind
@@ -398,7 +431,6 @@ gno_bwd_tc2_kernel(const GnoArgs a, const Tc2BwdLayout L, const float* __restric
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int row = tid & 127, half = tid >> 7;
-    float* bias = reinterpret_cast<float*>(sm + L.bias_base);
     uint8_t* A0 = sm + L.a0;
     uint8_t* DZ = sm + L.dz;
 
@@ -410,11 +442,10 @@ gno_bwd_tc2_kernel(const GnoArgs a, const Tc2BwdLayout L, const float* __restric
         for (int idx = tid; idx < N * KP; idx += B2T) {
             const int n = idx / KP, k = idx - n * KP;
             float v;
-            if (l == 0) v = k < 12 ? W[n * K + (k % 6)] : 0.f;
-            else v = W[n * K + k];
+            if (l == 0) v = k < 12 ? W[n * K + (k % 6)] : (k == 12 ? a.params[a.b_off[0] + n] : 0.f);
+            else v = k < K ? W[n * K + k] : (k == K ? a.params[a.b_off[l] + n] : 0.f);
             *reinterpret_cast<__nv_bfloat16*>(Ws + tc::cm_off(N, n, k)) = __float2bfloat16(v);
         }
-        for (int j = tid; j < N; j += B2T) bias[L.b_off[l] + j] = a.params[a.b_off[l] + j];
         if (l >= 1 && tid < T2E) {                 // constant ones / zero chunks of the activation tiles
             *reinterpret_cast<uint4*>(sm + L.h_off[l] + 8 * (128 * 16) + tid * 16) = make_uint4(0x00003F80u, 0u, 0u, 0u);
             *reinterpret_cast<uint4*>(sm + L.h_off[l] + 9 * (128 * 16) + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
@@ -422,6 +453,51 @@ gno_bwd_tc2_kernel(const GnoArgs a, const Tc2BwdLayout L, const float* __restric
     }
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, (uint32_t)L.tmem_cols);
     if (tid == 0) { tc::mbar_init(&mbar_mma, 1); tc::mbar_fence_init(); }
+
+    constexpr int Cout = 32, nc = 16;                       // output columns per thread
+    const bool use_f_mul = (a.transform == 0);
+    constexpr uint32_t KS128 = tc::kstep_kmajor(128);
+    const uint32_t sDZ = tc::smem_u32(DZ);
+    bool first_tile = true;
+
+    // layer-0 operand row [y hi | x hi | y lo | x lo | 1 | 0] in bf16 (the 1 is both the bias input of the recompute and
+    // the column that returns db_0 from the dW_0 GEMM; 0 for padding rows)
+    auto write_a0 = [&](const float (&c6)[6], bool valid) {
+        float hi[6], lo[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) { hi[j] = __bfloat162float(__float2bfloat16(c6[j])); lo[j] = c6[j] - hi[j]; }
+        uint4 c0, c1;
+        c0.x = tc::pack_bf16(hi[0], hi[1]); c0.y = tc::pack_bf16(hi[2], hi[3]);
+        c0.z = tc::pack_bf16(hi[4], hi[5]); c0.w = tc::pack_bf16(lo[0], lo[1]);
+        c1.x = tc::pack_bf16(lo[2], lo[3]); c1.y = tc::pack_bf16(lo[4], lo[5]);
+        c1.z = valid ? 0x00003F80u : 0u;
+        c1.w = 0u;
+        *reinterpret_cast<uint4*>(A0 + row * 16) = c0;
+        *reinterpret_cast<uint4*>(A0 + 128 * 16 + row * 16) = c1;
+    };
+    // loads only (no arithmetic on the results: a consumer would stall the in-order warp on the load latency)
+    auto load_row = [&](int src, int qry, float (&c6)[6], int& rb, int& re) {
+        if (half == 0) {
+            const float* py = a.y_pos + (size_t)src * 3;
+            const float* px = a.x_pos + (size_t)qry * 3;
+            c6[0] = py[0]; c6[1] = py[1]; c6[2] = py[2]; c6[3] = px[0]; c6[4] = px[1]; c6[5] = px[2];
+        }
+        rb = a.rowptr[qry]; re = a.rowptr[qry + 1];
+    };
+    auto inv_count = [&](int rb, int re, bool valid) { return !valid ? 0.f : (a.reduce == 0 ? 1.0f / (float)(re - rb) : 1.0f); };
+
+    // ---- first tile of this CTA: synchronous staging; later tiles are staged by the software pipeline below ----
+    int tile = blockIdx.x;
+    int src = 0, qry = 0;
+    float inv = 0.f;
+    if (tile < a.ntiles) {
+        const bool valid = row < min(T2E, a.E - tile * T2E);
+        float c6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int rb = 0, re = 1;
+        if (valid) { src = a.csr_src[tile * T2E + row]; qry = a.csr_qry[tile * T2E + row]; load_row(src, qry, c6, rb, re); }
+        inv = inv_count(rb, re, valid);
+        if (half == 0) write_a0(c6, valid);
+    }
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
@@ -430,45 +506,20 @@ gno_bwd_tc2_kernel(const GnoArgs a, const Tc2BwdLayout L, const float* __restric
     const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t ph_mma = 0;
 
-    constexpr int Cout = 32, nc = 16;                       // output columns per thread
-    const bool use_f_mul = (a.transform == 0);
-    constexpr uint32_t KS128 = tc::kstep_kmajor(128);
-    const uint32_t sDZ = tc::smem_u32(DZ);
-    bool first_tile = true;
-
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    for (; tile < a.ntiles; tile += gridDim.x) {
         const int e0 = tile * T2E;
         const int ne = min(T2E, a.E - e0);
         const bool valid = row < ne;
-        const int src = valid ? a.csr_src[e0 + row] : 0;
-        const int qry = valid ? a.csr_qry[e0 + row] : 0;
-        float inv = 0.f;
-        if (valid) inv = a.reduce == 0 ? 1.0f / (float)(a.rowptr[qry + 1] - a.rowptr[qry]) : 1.0f;
-        if (half == 0) {
-            float c6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (valid) {
-                const float* py = a.y_pos + (size_t)src * 3;
-                const float* px = a.x_pos + (size_t)qry * 3;
-                c6[0] = py[0]; c6[1] = py[1]; c6[2] = py[2]; c6[3] = px[0]; c6[4] = px[1]; c6[5] = px[2];
-            }
-            float hi[6], lo[6];
-#pragma unroll
-            for (int j = 0; j < 6; ++j) { hi[j] = __bfloat162float(__float2bfloat16(c6[j])); lo[j] = c6[j] - hi[j]; }
-            uint4 c0, c1;
-            c0.x = tc::pack_bf16(hi[0], hi[1]); c0.y = tc::pack_bf16(hi[2], hi[3]);
-            c0.z = tc::pack_bf16(hi[4], hi[5]); c0.w = tc::pack_bf16(lo[0], lo[1]);
-            c1.x = tc::pack_bf16(lo[2], lo[3]); c1.y = tc::pack_bf16(lo[4], lo[5]);
-            c1.z = valid ? 0x00003F80u : 0u;                   // K index 12 = 1.0: db_0 comes out of the dW_0 GEMM
-            c1.w = 0u;
-            *reinterpret_cast<uint4*>(A0 + row * 16) = c0;
-            *reinterpret_cast<uint4*>(A0 + 128 * 16 + row * 16) = c1;
-        }
-        tc::fence_async_smem();
-        tc::fence_before_sync();
-        __syncthreads();
+        // pipeline: indices of the next tile now, its coordinates / counts after the first layer, its operand row
+        // after the last MMA of this tile
+        const int ntile = tile + gridDim.x;
+        const bool nvalid = ntile < a.ntiles && row < min(T2E, a.E - ntile * T2E);
+        int nsrc = 0, nqry = 0;
+        float nc6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int nrb = 0, nre = 1;
 
         // =============== forward recompute: gelu AND gelu' ===============
-        float kv[nc];
+        float kv[nc], gr[nc], fr[nc];
 #pragma unroll
         for (int l = 0; l < NL; ++l) {
             const int N = a.dims[l + 1], KP = L.kpad[l];
@@ -485,12 +536,30 @@ gno_bwd_tc2_kernel(const GnoArgs a, const Tc2BwdLayout L, const float* __restric
                 }
                 __syncwarp();
             }
+            if (l == 0 && nvalid) { nsrc = a.csr_src[ntile * T2E + row]; nqry = a.csr_qry[ntile * T2E + row]; }
+            if (l == 1 && nvalid) load_row(nsrc, nqry, nc6, nrb, nre);
+            if (l == NL - 1) {
+                // d_out / f_y rows of this tile: issued before the wait on the last (GELU-free) layer
+                const float4* gp4 = reinterpret_cast<const float4*>(d_out + (size_t)qry * Cout + half * nc);
+                const float4* fp4 = reinterpret_cast<const float4*>(a.f_y + (size_t)src * Cout + half * nc);
+#pragma unroll
+                for (int j = 0; j < nc / 4; ++j) {
+                    const float4 t = valid ? gp4[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    gr[4 * j] = t.x; gr[4 * j + 1] = t.y; gr[4 * j + 2] = t.z; gr[4 * j + 3] = t.w;
+                }
+                if (use_f_mul) {
+#pragma unroll
+                    for (int j = 0; j < nc / 4; ++j) {
+                        const float4 t = valid ? fp4[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        fr[4 * j] = t.x; fr[4 * j + 1] = t.y; fr[4 * j + 2] = t.z; fr[4 * j + 3] = t.w;
+                    }
+                }
+            }
             tc::mbar_wait(&mbar_mma, ph_mma); ph_mma ^= 1;
             tc::fence_after_sync();
             if (l < NL - 1) {
                 float v[32];
                 tc::tmem_ld32(tlane + half * 32, v);
-                const float* bs = bias + L.b_off[l] + half * 32;
                 uint8_t* gpt = sm + L.gp_off[l + 1];
                 uint8_t* ht = sm + L.h_off[l + 1];
 #pragma unroll
@@ -499,9 +568,8 @@ gno_bwd_tc2_kernel(const GnoArgs a, const Tc2BwdLayout L, const float* __restric
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int c = c8 * 8 + 2 * j;
-                        const __half2 z = __floats2half2_rn(v[c] + bs[c], v[c + 1] + bs[c + 1]);
                         __half2 gg, dg;
-                        gelu_and_grad_h2(z, gg, dg);
+                        gelu_and_grad_h2(__floats2half2_rn(v[c], v[c + 1]), gg, dg);
                         og[j] = h2_to_bf16x2(gg);
                         od[j] = h2_as_u32(dg);
                     }
@@ -513,28 +581,14 @@ gno_bwd_tc2_kernel(const GnoArgs a, const Tc2BwdLayout L, const float* __restric
                 __syncthreads();
             } else {
                 tc::tmem_ld16(tlane + half * nc, kv);
-                const float* bs = bias + L.b_off[l] + half * nc;
-#pragma unroll
-                for (int c = 0; c < nc; ++c) kv[c] += bs[c];
             }
         }
 
-        // =============== output-side gradients (fp32), rows straight from global memory ===============
+        // =============== output-side gradients (fp32) ===============
         {
-            const float4* gp4 = reinterpret_cast<const float4*>(d_out + (size_t)qry * Cout + half * nc);
-            const float4* fp4 = reinterpret_cast<const float4*>(a.f_y + (size_t)src * Cout + half * nc);
-            float gr[nc], fr[nc];
 #pragma unroll
-            for (int j = 0; j < nc / 4; ++j) {
-                const float4 t = valid ? gp4[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-                gr[4 * j] = t.x * inv; gr[4 * j + 1] = t.y * inv; gr[4 * j + 2] = t.z * inv; gr[4 * j + 3] = t.w * inv;
-            }
+            for (int c = 0; c < nc; ++c) gr[c] *= inv;
             if (use_f_mul) {
-#pragma unroll
-                for (int j = 0; j < nc / 4; ++j) {
-                    const float4 t = valid ? fp4[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    fr[4 * j] = t.x; fr[4 * j + 1] = t.y; fr[4 * j + 2] = t.z; fr[4 * j + 3] = t.w;
-                }
                 if (d_f && valid) {
                     float* dst = d_f + (size_t)src * Cout + half * nc;
 #pragma unroll
@@ -609,6 +663,10 @@ gno_bwd_tc2_kernel(const GnoArgs a, const Tc2BwdLayout L, const float* __restric
             }
         }
         first_tile = false;
+        // every MMA of this tile has completed (A0 was last read by dW_0): stage the next tile's layer-0 operand
+        if (ntile < a.ntiles && half == 0) write_a0(nc6, nvalid);
+        src = nsrc; qry = nqry; inv = inv_count(nrb, nre, nvalid);
+        tc::fence_async_smem();
         tc::fence_before_sync();
         __syncthreads();
     }

@@ -28,6 +28,15 @@ def get_gno_precision() -> str:
     return "fp32" if _PRECISION["gno"] == 0 else "bf16"
 
 
+def set_node_mlp_tf32(on: bool = True) -> None:
+    """Node-level MLPs (lifting, projection, recovery, geo-embedding MLP) are torch fp32 GEMMs on [N_points, C]
+    tensors.  The reference's default mlp_type='channel' routes them through Conv1d, for which cuDNN allows TF32
+    (SURVEY.md appendix C.10); this switches the same tensor-core mode on for the Linear form as well.  It is
+    torch's process-wide flag pair -- the caller (bench.py, a trainer) decides."""
+    torch.backends.cuda.matmul.allow_tf32 = bool(on)
+    torch.backends.cudnn.allow_tf32 = bool(on)
+
+
 def _lib_():
     return _lib.load()
 
@@ -331,6 +340,34 @@ def geo_stats(source_pos, query_pos, csr: Csr, normalize: bool = True) -> torch.
     with torch.cuda.device(dev):
         check(lib.gaot_geo_stats(_p(sp), csr.n_src, _p(qp), csr.nq, _p(csr.rowptr), _p(csr.src), _p(feat),
                                  _stream(dev)), "geo_stats")
+        if normalize:
+            zscore_(feat)
+    return feat
+
+
+def geo_moments(source_pos, query_pos, csr: Csr) -> torch.Tensor:
+    """[nq, 12] per-query moment SUMS of (y - x) over this rank's sources (count, sum d, sum d^2, sum delta (3),
+    sum delta delta^T (6)); partials of disjoint source shards add up (sharded encoder)."""
+    _need_cuda(source_pos, query_pos)
+    sp, qp = _pos3(source_pos), _pos3(query_pos)
+    dev = qp.device
+    lib = _lib_()
+    mom = torch.empty(csr.nq, 12, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.gaot_geo_moments(_p(sp), csr.n_src, _p(qp), csr.nq, _p(csr.rowptr), _p(csr.src), _p(mom),
+                                   _stream(dev)), "geo_moments")
+    return mom
+
+
+def geo_from_moments(moments: torch.Tensor, normalize: bool = True) -> torch.Tensor:
+    """moment sums [nq, 12] -> the [nq, 9] statistical features of geo_stats (same finalisation code)."""
+    _need_cuda(moments)
+    mom = moments.to(torch.float32).contiguous()
+    dev = mom.device
+    lib = _lib_()
+    feat = torch.empty(mom.shape[0], 9, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.gaot_geo_from_moments(_p(mom), mom.shape[0], _p(feat), _stream(dev)), "geo_from_moments")
         if normalize:
             zscore_(feat)
     return feat

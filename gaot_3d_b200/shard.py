@@ -107,12 +107,34 @@ def local_encoder_edges(strategy: str, phys_local, latent_pos, radius: float, k:
     raise ValueError(f"Unknown encoder strategy: {strategy}")
 
 
+def sharded_encoder_geo_features(phys_local, latent_pos, enc_edges, group=None) -> torch.Tensor:
+    """Statistical geometric features [M, 9] of the latent tokens when their neighbours (physical points) are
+    sharded: local moment sums -> all-reduce(SUM) -> eigenvalues + z-score, identical on every rank
+    (reference geoembed.py:99-182 on the unsharded graph)."""
+    csr = ops.csr_of(enc_edges, phys_local.shape[0], latent_pos.shape[0])
+    mom = ops.geo_moments(phys_local, latent_pos, csr)
+    dist.all_reduce(mom, op=dist.ReduceOp.SUM, group=group)
+    return ops.geo_from_moments(mom, normalize=True)
+
+
+def global_zscore(feat_local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """z-score of row-sharded features over ALL rows (geoembed.py:177-180: mean, unbiased std, std < 1e-6 -> 1)."""
+    f64 = feat_local.double()
+    stats = torch.stack([f64.sum(0), (f64 * f64).sum(0)])
+    dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+    mean = stats[0] / n_total
+    var = ((stats[1] - n_total * mean * mean) / max(n_total - 1, 1)).clamp(min=0)
+    std = var.sqrt().float()
+    std = torch.where(std < 1e-6, torch.ones_like(std), std)
+    return (feat_local - mean.float()) / std
+
+
 def sharded_forward(model, batch_local, tokens_pos, n_total: int, group=None, enc_edges: Optional[torch.Tensor] = None):
     """GAOT3D forward on this rank's shard of ONE sample (batch of one).  Returns the local rows of
     the output [N_local, C_out].  `model` is a gaot_3d_b200.GAOT3D (single scale, use_gno=True)."""
     enc, dec = model.encoder, model.decoder
-    if len(enc.scales) != 1 or not enc.use_gno or enc.use_geoembed or dec.use_geoembed:
-        raise NotImplementedError("sharded path: single scale, GNO on, geometric embedding off (moment all-reduce is a later row)")
+    if len(enc.scales) != 1 or not enc.use_gno:
+        raise NotImplementedError("sharded path: single scale with the GNO enabled")
     from .layers.magno import _apply_node_mlp
     dev = batch_local.pos.device
     lat = tokens_pos.to(dev)
@@ -125,6 +147,11 @@ def sharded_forward(model, batch_local, tokens_pos, n_total: int, group=None, en
     cnt = torch.bincount(enc_edges[1], minlength=M).to(part.dtype)
     dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
     latent = all_reduce_forward(part, group) / cnt.clamp(min=1).unsqueeze(1)
+    if enc.use_geoembed:
+        # the neighbours of a latent token are spread over the ranks: all-reduce the moment SUMS, then every rank
+        # finishes (eigenvalues, z-score over all tokens) identically; coordinates carry no gradient
+        geo = enc.geoembed.mlp(sharded_encoder_geo_features(pos, lat, enc_edges, group))
+        latent = _apply_node_mlp(enc.recovery, enc.mlp_type, torch.cat([latent, geo], dim=-1))
     rn = model.process(latent.view(1, M, -1))
     rn = all_reduce_backward(rn.reshape(M, -1), group)
     if dec.decoder_strategy == "reverse":            # flip of the *bidirectional* encoder graph (magno.py:263-273)
@@ -135,6 +162,11 @@ def sharded_forward(model, batch_local, tokens_pos, n_total: int, group=None, en
         from .graph import get_neighbor_strategy
         dec_edges = get_neighbor_strategy(dec.decoder_strategy, pos, None, lat, None, dec.gno_radius, dec.k_neighbors, True)
     out = dec.gno(y_pos=lat, x_pos=pos, edge_index=dec_edges, f_y=rn)
+    if dec.use_geoembed:
+        # queries are sharded, their neighbours (latents) are not: local statistics, global z-score
+        raw = dec.geoembed.statistical_features(lat, pos, dec_edges, normalize=False)
+        geo = dec.geoembed.mlp(global_zscore(raw, n_total, group))
+        out = _apply_node_mlp(dec.recovery, dec.mlp_type, torch.cat([out, geo], dim=-1))
     return _apply_node_mlp(dec.projection, dec.mlp_type, out)
 
 

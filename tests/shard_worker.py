@@ -20,7 +20,8 @@ def main():
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", device_id=dev)
     ok = True
-    for strat in (["radius", "reverse"], "knn", ["bidirectional", "radius"]):
+    for strat, geo in ((["radius", "reverse"], [False, False]), ("knn", [False, False]), (["bidirectional", "radius"], [False, False]),
+                       ("bidirectional", [True, False]), (["radius", "knn"], [True, True])):
         torch.manual_seed(0)
         N, grid, r, k = 40000, (16, 16, 8), 0.12, 2
         pos = torch.from_numpy(synth.surface_cloud(N, seed=1)).to(dev)
@@ -28,7 +29,7 @@ def main():
         tgt = torch.randn(N, 4, device=dev)
         lat = torch.from_numpy(synth.latent_grid(grid)).to(dev)
         mc = G.MAGNOConfig(gno_coord_dim=3, lifting_channels=32, neighbor_strategy=strat, gno_radius=r, mlp_type="linear",
-                           precompute_edges=False, use_geoembed=[False, False], encoder_feature_attr=["pos", "c"], k_neighbors=k)
+                           precompute_edges=False, use_geoembed=geo, encoder_feature_attr=["pos", "c"], k_neighbors=k)
         tc = G.TransformerConfig(patch_size=2, hidden_size=128, num_layers=2, positional_embedding="rope")
         tc.attn_config.hidden_size, tc.attn_config.num_heads, tc.attn_config.num_kv_heads = 128, 4, 4
         tc.attn_config.atten_dropout = 0.0
@@ -59,7 +60,7 @@ def main():
         good = e_out < 2e-2 and e_loss < 1e-3 and worst < 5e-2
         ok &= good
         if rank == 0:
-            print(f"strategy={strat}: out rel err {e_out:.2e}, loss rel err {e_loss:.2e}, worst grad rel l2 {worst:.2e} -> {'OK' if good else 'FAIL'}", flush=True)
+            print(f"strategy={strat} geoembed={geo}: out rel err {e_out:.2e}, loss rel err {e_loss:.2e}, worst grad rel l2 {worst:.2e} -> {'OK' if good else 'FAIL'}", flush=True)
         model.zero_grad(set_to_none=True)
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

@@ -6,6 +6,7 @@ import numpy as np
 BOXES = {
     "drivaernet": ([-1.16, -1.20, 0.0], [4.21, 1.19, 1.77]),      # reference src/data/metadata.py:32
     "drivaerml": ([-0.943, -1.14, -0.318], [4.14, 1.14, 1.25]),   # metadata.py:117
+    "crm": ([2.3495, -29.460142, 2.3101413], [66.744965, 29.460142, 8.833843]),   # NASA CRM, metadata.py:66
     "unit": ([-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]),
 }
 
@@ -37,3 +38,9 @@ def unit_normals(n, seed=0):
     rng = np.random.default_rng(seed + 1000)
     v = rng.normal(size=(n, 3))
     return (v / np.linalg.norm(v, axis=1, keepdims=True)).astype(np.float32)
+
+
+def mach_aoa(n, seed=0):
+    """NASA-CRM condition features: one (Mach, AOA) pair per sample, broadcast to every point (metadata.py:73)."""
+    rng = np.random.default_rng(seed + 2000)
+    return np.tile(np.array([[rng.uniform(0.7, 0.9), rng.uniform(0.0, 4.0)]], dtype=np.float32), (n, 1))

@@ -199,3 +199,35 @@ def test_gno_bf16_tensor_core_path(strategy, dec):
     for i in range(len(bs)):
         e = ((bd[i].grad.double().cpu() - br2[i].grad).norm() / br2[i].grad.norm()).item()
         assert e < 2e-2, (f"db{i}", e)
+
+
+def test_geo_moments_compose_over_source_shards():
+    """Sharded-encoder statistics: moment sums of two disjoint physical-point shards add up to
+    the moments of the whole cloud, and finishing them gives the features of the fused single-pass kernel."""
+    from gaot_3d_b200 import ops
+    phys, lat = synth.surface_cloud(20000, seed=5), synth.latent_grid((12, 12, 12))
+    ei = torch.from_numpy(og.radius_np(phys, lat, 0.2, workers=-1)[::-1].copy())            # [phys, latent]
+    P, L = torch.from_numpy(phys).to(DEV), torch.from_numpy(lat).to(DEV)
+    csr = ops.build_csr(ei[0].to(DEV), ei[1].to(DEV), P.shape[0], L.shape[0])
+    whole = ops.geo_stats(P, L, csr, normalize=False)
+    mom = ops.geo_moments(P, L, csr)
+    assert torch.equal(ops.geo_from_moments(mom, normalize=False), whole)                  # same code, same bits
+    cut = 9000
+    parts = []
+    for lo, hi in ((0, cut), (cut, P.shape[0])):
+        m = (ei[0] >= lo) & (ei[0] < hi)
+        e = ei[:, m].clone()
+        e[0] -= lo
+        c = ops.build_csr(e[0].to(DEV), e[1].to(DEV), hi - lo, L.shape[0])
+        parts.append(ops.geo_moments(P[lo:hi].contiguous(), L, c))
+    both = ops.geo_from_moments(parts[0] + parts[1], normalize=False)
+    ref = ogno.geo_statistical_features(torch.from_numpy(phys).double(), torch.from_numpy(lat).double(), ei, normalize=False)
+    assert torch.equal(both[:, 0], whole[:, 0])                                              # counts are exact
+    close(both[:, :6], ref[:, :6], rtol=1e-4, atol_rel=1e-5, what="sharded moments")
+    close(both[:, 6:], ref[:, 6:], rtol=1e-3, atol_rel=1e-4, what="sharded eigenvalues")
+    # z-scored features, then the decoder-side global z-score of row shards
+    from gaot_3d_b200 import shard
+    import torch.distributed as dist
+    z = ops.geo_from_moments(parts[0] + parts[1], normalize=True)
+    zr = ogno.geo_statistical_features(torch.from_numpy(phys).double(), torch.from_numpy(lat).double(), ei, normalize=True)
+    close(z, zr, rtol=2e-3, atol_rel=2e-4, what="z-scored features")

@@ -70,6 +70,13 @@ def _worker(rank, world, port, ret):
         pg2 = torch.cat([p.grad.reshape(-1) for p in ws2 + bs2])
         assert torch.allclose(pg, pg2, rtol=1e-3, atol=1e-6), "param grads"
         assert torch.allclose(mix.grad, mix2.grad, rtol=1e-3, atol=1e-6), "replicated-part grad is already total"
+        # --- decoder-side geometric embedding: z-score of row-sharded features over ALL rows (geoembed.py:177-180)
+        feats = torch.randn(N, 9, generator=torch.Generator().manual_seed(5)) * torch.arange(1, 10) + 3.0
+        feats[:, 4] = 2.5                                                    # constant column: std < 1e-6 -> 1
+        zl = shard.global_zscore(feats[lo:hi], N)
+        std = feats.std(dim=0)
+        zf = (feats - feats.mean(dim=0)) / torch.where(std < 1e-6, torch.ones_like(std), std)
+        assert torch.allclose(zl, zf[lo:hi], rtol=1e-4, atol=1e-5), "global z-score"
         ret[rank] = "ok"
     except Exception as e:  # pragma: no cover
         import traceback
