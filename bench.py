@@ -113,6 +113,45 @@ def run_cpu_arm(wl, steps, warmup, name):
     return sec, cores, sample, last["parts"]
 
 
+def gno_large_graph(lib, G, pos, lat, dev, pk_hbm, precision, radius=0.033):
+    """GNO edges/s where the kernel, not the launch, is what is timed: the radius graphs of the same cloud
+    (decoder: every point -> latents within r, ~12 edges per point; encoder: capped at 32 per latent), fused
+    GNO forward and backward timed by the in-library CUDA events (outside the step timing)."""
+    import ctypes
+    from gaot_3d_b200 import ops
+    out = {}
+    for name, dec, layers in (("decoder_radius", True, [6, 64, 64, C_LIFT]), ("encoder_radius", False, [6, 64, 64, 64, C_LIFT])):
+        ei = G.get_neighbor_strategy("radius", pos, None, lat, None, radius, 1, dec)
+        ypos, xpos = (lat, pos) if dec else (pos, lat)
+        torch.manual_seed(1)
+        ws = [(torch.randn(layers[i + 1], layers[i], device=dev) / layers[i] ** 0.5).requires_grad_(True) for i in range(len(layers) - 1)]
+        bs = [torch.zeros(layers[i + 1], device=dev, requires_grad=True) for i in range(len(layers) - 1)]
+        f_y = torch.randn(ypos.shape[0], C_LIFT, device=dev, requires_grad=True)
+        csr = ops.csr_of(ei, ypos.shape[0], xpos.shape[0])
+        go = torch.randn(xpos.shape[0], C_LIFT, device=dev)
+        for _ in range(3):
+            ops.gno(ypos, xpos, f_y, csr, ws, bs, precision=precision).backward(go)
+        lib.gaot_profile_enable(1)
+        for _ in range(5):
+            ops.gno(ypos, xpos, f_y, csr, ws, bs, precision=precision).backward(go)
+        buf = ctypes.create_string_buffer(1 << 14)
+        lib.gaot_profile_summary(buf, len(buf))
+        lib.gaot_profile_enable(0)
+        E = int(ei.shape[1])
+        rec = {"edges": E, "mlp": layers}
+        for line in buf.value.decode().strip().splitlines():
+            nm, calls, ms, work = line.split()
+            if nm in ("gno_fwd", "gno_bwd"):
+                t = float(ms) / int(calls) * 1e-3
+                rec[nm + "_ms"] = t * 1e3
+                rec[nm + "_edges_per_s"] = E / t
+                rec[nm + "_hbm_frac"] = float(work) / int(calls) / t / 1e9 / pk_hbm       # algorithmic bytes (SURVEY 8d) / measured copy peak
+        if "gno_fwd_ms" in rec and "gno_bwd_ms" in rec:
+            rec["fwd_bwd_edges_per_s"] = E / ((rec["gno_fwd_ms"] + rec["gno_bwd_ms"]) * 1e-3)
+        out[name] = rec
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -272,6 +311,8 @@ def main():
     lib.gaot_profile_enable(0)
     clk = clocks.stop()
     ms_e2e = timed(args.steps, e2e=True)
+    gno_large = gno_large_graph(lib, G, resident[0][0], lat, dev, pk_hbm=peaks()["hbm"], precision=args.gno_precision) \
+        if (world == 1 and wl["n_points"] <= 1_000_000) else None
 
     ms_step = ms_total / args.steps
     samples_per_step = 1 if (args.shard and world > 1) else world
@@ -320,6 +361,8 @@ def main():
            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                    "ms_per_step": ms_e2e / args.steps},
            "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "gno_edges_per_s": gno}
+    if gno_large:
+        out["gno_edges_per_s"]["large_graphs"] = gno_large
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             try:

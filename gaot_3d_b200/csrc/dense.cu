@@ -19,6 +19,8 @@
 #include "common.cuh"
 #include "tc05.cuh"
 #include <algorithm>
+#include <cstdlib>
+#include <cuda.h>
 
 namespace gaot {
 
@@ -431,6 +433,215 @@ static int launch_gemm2(const GemmArgs& g, cudaStream_t st) {
     return GAOT_OK;
 }
 
+// =====================================================================================================
+// gemm3: the same warp-specialised persistent GEMM with the operand tiles moved by the TMA engine.
+// What ncu said about gemm2 (profiles/r01f_gemm2_*): 47 % of the stall samples are the loader warps waiting
+// on LDG (each loader keeps 8 x 16 B in flight: ~30 KB per SM against the ~120 KB that L2 latency x bandwidth
+// asks for), and most launches have <= 1 tile per CTA, so nothing hides that latency.  Here ONE lane issues
+// cp.async.bulk.tensor for a whole [128 x 64] bf16 box per operand and K block (32 KB per stage in flight per
+// request pair, no registers, no generic->async proxy fence); the boxes land in the 128-byte-swizzled
+// canonical layouts that tcgen05.mma reads directly:
+//   K-major operand  (rows = M/N, 64 contraction elements = 128 B per row): SBO = 1024 B (8-row groups),
+//                    K16 step = +32 B inside the swizzle atom
+//   MN-major operand (rows = contraction, 64 M/N elements = 128 B per row; two boxes for 128 columns):
+//                    LBO = 8192 B (next 64-wide M/N block), SBO = 1024 B (next 8 contraction rows),
+//                    K16 step = +2048 B
+// (cute::UMMA canonical layouts, mma_traits_sm100.hpp make_umma_desc; layout_type SWIZZLE_128B = 2.)
+// 3-stage ring, 2 CTAs/SM, accumulator double-buffered in TMEM, epilogue as in gemm2.
+// =====================================================================================================
+namespace dn3 {
+constexpr int STAGES = 3, THREADS = 192;          // warp 0: TMA producer lane, warp 1: MMA lane, warps 2..5: epilogue
+constexpr uint32_t OP_BYTES = 128 * 64 * 2;       // one operand tile (16 KB)
+constexpr uint32_t STAGE_BYTES = 2 * OP_BYTES;
+constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024;     // + slack for the 1024-byte alignment of the ring
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled tensor_map_encoder() {
+    static PFN_encodeTiled fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (PFN_encodeTiled)p;
+    }();
+    return fn;
+}
+
+// row-major bf16 matrix [rows, cols] with leading dimension ld (elements); box = 64 contiguous elements x box_rows rows
+static bool make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    PFN_encodeTiled enc = tensor_map_encoder();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1u, 1u};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tm, int c_inner, int c_outer, uint64_t* mbar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+                 ::"r"(smem_dst), "l"(tm), "r"(c_inner), "r"(c_outer), "r"(tc::smem_u32(mbar)) : "memory");
+}
+// shared-memory matrix descriptor, SWIZZLE_128B (layout_type 2 in bits 61..63), version 1
+__device__ __forceinline__ tc::Desc make_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return tc::Desc{((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16),
+                    ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29)};
+}
+
+template <bool B_MN>
+__global__ void __launch_bounds__(dn3::THREADS, 2)
+gemm3_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int tiles_n, int total_tiles) {
+    extern __shared__ __align__(1024) uint8_t sm_raw[];
+    __shared__ uint64_t full[dn3::STAGES], empty[dn3::STAGES], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nkb = (int)((g.K + dn::BK - 1) / dn::BK);
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 256);
+    if (tid == 32) {
+#pragma unroll
+        for (int s = 0; s < dn3::STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+#pragma unroll
+        for (int b = 0; b < 2; ++b) { tc::mbar_init(&acc_full[b], 1); tc::mbar_init(&acc_empty[b], 4); }
+        tc::mbar_fence_init();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t sm_base = (tc::smem_u32(sm_raw) + 1023u) & ~1023u;
+    const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (one lane)
+        if (tc::elect_one()) {
+            int G = 0;
+            for (int t = 0; t < my_tiles; ++t) {
+                const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+                const int m0 = (tile / tiles_n) * dn::BM, n0 = (tile % tiles_n) * dn::BN;
+                for (int kb = 0; kb < nkb; ++kb, ++G) {
+                    const int s = G % dn3::STAGES;
+                    if (G >= dn3::STAGES) tc::mbar_wait(&empty[s], (uint32_t)(((G / dn3::STAGES) - 1) & 1));
+                    const uint32_t sa = sm_base + s * dn3::STAGE_BYTES, sb = sa + dn3::OP_BYTES;
+                    tc::mbar_arrive_expect_tx(&full[s], dn3::STAGE_BYTES);
+                    const int k0 = kb * dn::BK;
+                    tma_load_2d(sa, &tmA, k0, m0, &full[s]);
+                    if (B_MN) {
+                        tma_load_2d(sb, &tmB, n0, k0, &full[s]);                     // [64 contraction rows x 64 columns] x 2
+                        tma_load_2d(sb + dn3::OP_BYTES / 2, &tmB, n0 + 64, k0, &full[s]);
+                    } else {
+                        tma_load_2d(sb, &tmB, k0, n0, &full[s]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ tensor-core issue (one lane)
+        if (tc::elect_one()) {
+            constexpr uint32_t idesc = tc::make_idesc_bf16(dn::BM, dn::BN, 0, B_MN ? 1 : 0);
+            constexpr uint32_t B_LBO = B_MN ? dn3::OP_BYTES / 2 : 16u, B_KSTEP = B_MN ? 2048u : 32u;
+            int G = 0;
+            for (int t = 0; t < my_tiles; ++t) {
+                const int buf = t & 1;
+                if (t >= 2) { tc::mbar_wait(&acc_empty[buf], (uint32_t)(((t - 2) >> 1) & 1)); tc::fence_after_sync(); }
+                for (int kb = 0; kb < nkb; ++kb, ++G) {
+                    const int s = G % dn3::STAGES;
+                    tc::mbar_wait(&full[s], (uint32_t)((G / dn3::STAGES) & 1));
+                    tc::fence_after_sync();
+                    const tc::Desc dA = make_desc_sw128(sm_base + s * dn3::STAGE_BYTES, 16u, 1024u);
+                    const tc::Desc dB = make_desc_sw128(sm_base + s * dn3::STAGE_BYTES + dn3::OP_BYTES, B_LBO, 1024u);
+#pragma unroll
+                    for (int ks = 0; ks < dn::BK / 16; ++ks)
+                        tc::mma_bf16(tmem + (uint32_t)buf * 128u, dA.adv(ks * 32u).u64(), dB.adv(ks * B_KSTEP).u64(), idesc, (kb | ks) != 0);
+                    tc::mma_commit(&empty[s]);
+                }
+                tc::mma_commit(&acc_full[buf]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ epilogue: TMEM lane quarter = warp & 3
+        const int lg = warp & 3;
+        for (int t = 0; t < my_tiles; ++t) {
+            const int tile = (int)blockIdx.x + t * (int)gridDim.x, buf = t & 1;
+            const int64_t m0 = (int64_t)(tile / tiles_n) * dn::BM, n0 = (int64_t)(tile % tiles_n) * dn::BN;
+            const int64_t row = m0 + lg * 32 + lane;
+            tc::mbar_wait(&acc_full[buf], (uint32_t)((t >> 1) & 1));
+            tc::fence_after_sync();
+#pragma unroll 1
+            for (int c0 = 0; c0 < dn::BN; c0 += 32) {
+                float v[32];
+                tc::tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)buf * 128u + c0, v);
+                const int64_t col = n0 + c0;
+                if (row < g.M && col < g.N) {          // N is a multiple of 32 on this path (checked by the host)
+                    if (g.bias) {
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + col + c));
+                            v[c] += b.x; v[c + 1] += b.y; v[c + 2] += b.z; v[c + 3] += b.w;
+                        }
+                    }
+                    if (g.residual) {
+                        const float* rp = g.residual + row * g.ldr + col;
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4) {
+                            const float4 r = __ldg(reinterpret_cast<const float4*>(rp + c));
+                            v[c] += r.x; v[c + 1] += r.y; v[c + 2] += r.z; v[c + 3] += r.w;
+                        }
+                    }
+                    if (g.c_bf16) {
+                        bf16* cp = reinterpret_cast<bf16*>(g.C) + row * g.ldc + col;
+#pragma unroll
+                        for (int c = 0; c < 32; c += 8) {
+                            uint4 o;
+                            o.x = tc::pack_bf16(v[c], v[c + 1]); o.y = tc::pack_bf16(v[c + 2], v[c + 3]);
+                            o.z = tc::pack_bf16(v[c + 4], v[c + 5]); o.w = tc::pack_bf16(v[c + 6], v[c + 7]);
+                            *reinterpret_cast<uint4*>(cp + c) = o;
+                        }
+                    } else {
+                        float* cp = reinterpret_cast<float*>(g.C) + row * g.ldc + col;
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(cp + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+                    }
+                }
+            }
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 256);
+}
+
+// returns GAOT_ERR_UNSUPPORTED when the operands do not meet the TMA constraints (caller falls back to gemm2)
+template <bool B_MN>
+static int launch_gemm3(const GemmArgs& g, cudaStream_t st) {
+    static bool attr_done = false;
+    auto kern = gemm3_kernel<B_MN>;
+    if (((uintptr_t)g.A | (uintptr_t)g.B) & 15) return GAOT_ERR_UNSUPPORTED;
+    CUtensorMap tmA, tmB;
+    if (!make_tmap(&tmA, g.A, g.M, g.K, g.lda, 128)) return GAOT_ERR_UNSUPPORTED;
+    // B: K-major -> matrix [N, K] (box 128 rows); MN-major -> matrix [K, N] (box 64 contraction rows, two boxes per tile)
+    if (!(B_MN ? make_tmap(&tmB, g.B, g.K, g.N, g.ldb, 64) : make_tmap(&tmB, g.B, g.N, g.K, g.ldb, 128))) return GAOT_ERR_UNSUPPORTED;
+    if (!attr_done) {
+        GAOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dn3::SMEM_BYTES));
+        attr_done = true;
+    }
+    const int tiles_n = (int)((g.N + dn::BN - 1) / dn::BN), tiles_m = (int)((g.M + dn::BM - 1) / dn::BM);
+    const int total = tiles_n * tiles_m;
+    const int grid = std::min(total, 2 * kNumSMs);
+    kern<<<grid, dn3::THREADS, dn3::SMEM_BYTES, st>>>(g, tmA, tmB, tiles_n, total);
+    GAOT_LAUNCH_CHECK();
+    return GAOT_OK;
+}
+
 // fixed-order sum of the split-K partials (+ bias / accumulate): deterministic weight gradients
 __global__ void __launch_bounds__(256)
 gemm_splitk_reduce_kernel(const float* __restrict__ part, int splits, int64_t M, int64_t N, const float* __restrict__ bias,
@@ -505,8 +716,15 @@ static int run_gemm(GemmArgs g, int a_dtype, int b_dtype, bool a_mn, bool b_mn, 
     int rc;
     {   // persistent warp-specialised kernel for bf16 K-major-A products (GAOT_GEMM_OLD=1 selects the one-tile kernel)
         static const bool use_old = getenv("GAOT_GEMM_OLD") && atoi(getenv("GAOT_GEMM_OLD")) != 0;
-        if (!use_old && a_dtype && b_dtype && !a_mn && !g.A2 && !g.accumulate && splits == 1 && g.N % 32 == 0)
+        // GAOT_GEMM_GEN=2 pins the register-staged gemm2 (A/B timing); default: the TMA-fed gemm3 when the operands allow it
+        static const bool no_tma = getenv("GAOT_GEMM_GEN") && atoi(getenv("GAOT_GEMM_GEN")) == 2;
+        if (!use_old && a_dtype && b_dtype && !a_mn && !g.A2 && !g.accumulate && splits == 1 && g.N % 32 == 0) {
+            if (!no_tma && g.K % dn::BK == 0 && g.N % dn::BN == 0 && g.M >= dn::BM) {
+                rc = b_mn ? launch_gemm3<true>(g, st) : launch_gemm3<false>(g, st);
+                if (rc != GAOT_ERR_UNSUPPORTED) return rc;
+            }
             return b_mn ? launch_gemm2<true>(g, st) : launch_gemm2<false>(g, st);
+        }
     }
     const int sel = (a_dtype ? 8 : 0) | (b_dtype ? 4 : 0) | (a_mn ? 2 : 0) | (b_mn ? 1 : 0);
     switch (sel) {

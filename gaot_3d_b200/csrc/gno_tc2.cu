@@ -518,6 +518,20 @@ gno_bwd_tc2_kernel(const GnoArgs a, const Tc2BwdLayout L, const float* __restric
         float nc6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         int nrb = 0, nre = 1;
 
+        // source feature rows -> dZ buffer (free until the output stage): 8 lanes per 128-byte row, 16-byte pieces
+        // XOR-swizzled by the row so that the row-per-thread reads below are conflict-free
+        if (use_f_mul) {
+            const int wr = (warp & 3) * 32;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int r = (half * 4 + j) * 4 + (lane >> 3);
+                const int sr = __shfl_sync(0xffffffffu, src, r);
+                tc::cp_async16(sDZ + (uint32_t)(wr + r) * 128u + (uint32_t)(((lane & 7) ^ ((wr + r) & 7)) * 16),
+                               a.f_y + (size_t)sr * Cout + (lane & 7) * 4, wr + r < ne);
+            }
+            tc::cp_async_commit();
+        }
+
         // =============== forward recompute: gelu AND gelu' ===============
         float kv[nc], gr[nc], fr[nc];
 #pragma unroll
@@ -538,22 +552,25 @@ gno_bwd_tc2_kernel(const GnoArgs a, const Tc2BwdLayout L, const float* __restric
             }
             if (l == 0 && nvalid) { nsrc = a.csr_src[ntile * T2E + row]; nqry = a.csr_qry[ntile * T2E + row]; }
             if (l == 1 && nvalid) load_row(nsrc, nqry, nc6, nrb, nre);
-            if (l == NL - 1) {
-                // d_out / f_y rows of this tile: issued before the wait on the last (GELU-free) layer
+            if (l == (NL >= 3 ? NL - 2 : NL - 1)) {
+                // d_out rows of this tile (query-major CSR: neighbouring edges share them), issued one layer early
                 const float4* gp4 = reinterpret_cast<const float4*>(d_out + (size_t)qry * Cout + half * nc);
-                const float4* fp4 = reinterpret_cast<const float4*>(a.f_y + (size_t)src * Cout + half * nc);
 #pragma unroll
                 for (int j = 0; j < nc / 4; ++j) {
                     const float4 t = valid ? gp4[j] : make_float4(0.f, 0.f, 0.f, 0.f);
                     gr[4 * j] = t.x; gr[4 * j + 1] = t.y; gr[4 * j + 2] = t.z; gr[4 * j + 3] = t.w;
                 }
-                if (use_f_mul) {
+            }
+            if (l == NL - 1 && use_f_mul) {
+                // f_y rows were gathered into the (still unused) dZ buffer at the top of the tile; the barrier after the
+                // previous layer made them visible.  Everyone must have its copy before dZ is written below.
+                const int sw = row & 7;
 #pragma unroll
-                    for (int j = 0; j < nc / 4; ++j) {
-                        const float4 t = valid ? fp4[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-                        fr[4 * j] = t.x; fr[4 * j + 1] = t.y; fr[4 * j + 2] = t.z; fr[4 * j + 3] = t.w;
-                    }
+                for (int j = 0; j < nc / 4; ++j) {
+                    const float4 t = *reinterpret_cast<const float4*>(DZ + row * 128 + (((half * 4 + j) ^ sw) * 16));
+                    fr[4 * j] = t.x; fr[4 * j + 1] = t.y; fr[4 * j + 2] = t.z; fr[4 * j + 3] = t.w;
                 }
+                __syncthreads();
             }
             tc::mbar_wait(&mbar_mma, ph_mma); ph_mma ^= 1;
             tc::fence_after_sync();
@@ -576,6 +593,7 @@ gno_bwd_tc2_kernel(const GnoArgs a, const Tc2BwdLayout L, const float* __restric
                     *reinterpret_cast<uint4*>(ht + (half * 4 + c8) * (128 * 16) + row * 16) = make_uint4(og[0], og[1], og[2], og[3]);
                     *reinterpret_cast<uint4*>(gpt + (half * 4 + c8) * (128 * 16) + row * 16) = make_uint4(od[0], od[1], od[2], od[3]);
                 }
+                if (l == NL - 2) tc::cp_async_wait_all();          // this thread's pieces of the f_y gather have landed
                 tc::fence_async_smem();
                 tc::fence_before_sync();
                 __syncthreads();
