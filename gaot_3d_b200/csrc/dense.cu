@@ -493,14 +493,16 @@ __device__ __forceinline__ tc::Desc make_desc_sw128(uint32_t saddr, uint32_t lbo
                     ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29)};
 }
 
-template <bool B_MN>
+template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(dn3::THREADS, 2)
-gemm3_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int tiles_n, int total_tiles) {
+gemm3_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int tiles_n, int tiles_mn,
+             int total_tiles) {
     extern __shared__ __align__(1024) uint8_t sm_raw[];
     __shared__ uint64_t full[dn3::STAGES], empty[dn3::STAGES], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nkb = (int)((g.K + dn::BK - 1) / dn::BK);
+    // work item = (output tile, K split): item / tiles_mn is the split, whose K blocks are [z * kb_per_split, ...)
+    const int nkb_all = (int)((g.K + dn::BK - 1) / dn::BK);
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, 256);
     if (tid == 32) {
 #pragma unroll
@@ -521,15 +523,22 @@ gemm3_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap tmA, const __
         if (tc::elect_one()) {
             int G = 0;
             for (int t = 0; t < my_tiles; ++t) {
-                const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+                const int item = (int)blockIdx.x + t * (int)gridDim.x;
+                const int z = item / tiles_mn, tile = item - z * tiles_mn;
                 const int m0 = (tile / tiles_n) * dn::BM, n0 = (tile % tiles_n) * dn::BN;
-                for (int kb = 0; kb < nkb; ++kb, ++G) {
+                const int kb0 = z * g.kb_per_split, kb1 = min(nkb_all, kb0 + g.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb, ++G) {
                     const int s = G % dn3::STAGES;
                     if (G >= dn3::STAGES) tc::mbar_wait(&empty[s], (uint32_t)(((G / dn3::STAGES) - 1) & 1));
                     const uint32_t sa = sm_base + s * dn3::STAGE_BYTES, sb = sa + dn3::OP_BYTES;
                     tc::mbar_arrive_expect_tx(&full[s], dn3::STAGE_BYTES);
                     const int k0 = kb * dn::BK;
-                    tma_load_2d(sa, &tmA, k0, m0, &full[s]);
+                    if (A_MN) {
+                        tma_load_2d(sa, &tmA, m0, k0, &full[s]);                     // [64 contraction rows x 64 columns] x 2
+                        tma_load_2d(sa + dn3::OP_BYTES / 2, &tmA, m0 + 64, k0, &full[s]);
+                    } else {
+                        tma_load_2d(sa, &tmA, k0, m0, &full[s]);
+                    }
                     if (B_MN) {
                         tma_load_2d(sb, &tmB, n0, k0, &full[s]);                     // [64 contraction rows x 64 columns] x 2
                         tma_load_2d(sb + dn3::OP_BYTES / 2, &tmB, n0 + 64, k0, &full[s]);
@@ -543,21 +552,24 @@ gemm3_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap tmA, const __
     } else if (warp == 1) {
         // ------------------------------------------------------------------ tensor-core issue (one lane)
         if (tc::elect_one()) {
-            constexpr uint32_t idesc = tc::make_idesc_bf16(dn::BM, dn::BN, 0, B_MN ? 1 : 0);
+            constexpr uint32_t idesc = tc::make_idesc_bf16(dn::BM, dn::BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+            constexpr uint32_t A_LBO = A_MN ? dn3::OP_BYTES / 2 : 16u, A_KSTEP = A_MN ? 2048u : 32u;
             constexpr uint32_t B_LBO = B_MN ? dn3::OP_BYTES / 2 : 16u, B_KSTEP = B_MN ? 2048u : 32u;
             int G = 0;
             for (int t = 0; t < my_tiles; ++t) {
                 const int buf = t & 1;
+                const int z = ((int)blockIdx.x + t * (int)gridDim.x) / tiles_mn;
+                const int kb0 = z * g.kb_per_split, nkb = min(nkb_all, kb0 + g.kb_per_split) - kb0;
                 if (t >= 2) { tc::mbar_wait(&acc_empty[buf], (uint32_t)(((t - 2) >> 1) & 1)); tc::fence_after_sync(); }
                 for (int kb = 0; kb < nkb; ++kb, ++G) {
                     const int s = G % dn3::STAGES;
                     tc::mbar_wait(&full[s], (uint32_t)((G / dn3::STAGES) & 1));
                     tc::fence_after_sync();
-                    const tc::Desc dA = make_desc_sw128(sm_base + s * dn3::STAGE_BYTES, 16u, 1024u);
+                    const tc::Desc dA = make_desc_sw128(sm_base + s * dn3::STAGE_BYTES, A_LBO, 1024u);
                     const tc::Desc dB = make_desc_sw128(sm_base + s * dn3::STAGE_BYTES + dn3::OP_BYTES, B_LBO, 1024u);
 #pragma unroll
                     for (int ks = 0; ks < dn::BK / 16; ++ks)
-                        tc::mma_bf16(tmem + (uint32_t)buf * 128u, dA.adv(ks * 32u).u64(), dB.adv(ks * B_KSTEP).u64(), idesc, (kb | ks) != 0);
+                        tc::mma_bf16(tmem + (uint32_t)buf * 128u, dA.adv(ks * A_KSTEP).u64(), dB.adv(ks * B_KSTEP).u64(), idesc, (kb | ks) != 0);
                     tc::mma_commit(&empty[s]);
                 }
                 tc::mma_commit(&acc_full[buf]);
@@ -568,17 +580,45 @@ gemm3_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap tmA, const __
         // ------------------------------------------------------------------ epilogue: TMEM lane quarter = warp & 3
         const int lg = warp & 3;
         for (int t = 0; t < my_tiles; ++t) {
-            const int tile = (int)blockIdx.x + t * (int)gridDim.x, buf = t & 1;
+            const int item = (int)blockIdx.x + t * (int)gridDim.x, buf = t & 1;
+            const int z = item / tiles_mn, tile = item - z * tiles_mn;
             const int64_t m0 = (int64_t)(tile / tiles_n) * dn::BM, n0 = (int64_t)(tile % tiles_n) * dn::BN;
             const int64_t row = m0 + lg * 32 + lane;
+            // the residual rows of this tile are requested BEFORE the wait on the accumulator (two 32-column groups in
+            // flight, refilled while the previous group is written): their latency hides behind the main loop
+            float4 rr[2][8];
+            const float* rrow = g.residual ? g.residual + row * g.ldr + n0 : nullptr;
+            if (rrow && row < g.M) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) rr[q][c] = __ldg(reinterpret_cast<const float4*>(rrow + q * 32) + c);
+            }
             tc::mbar_wait(&acc_full[buf], (uint32_t)((t >> 1) & 1));
             tc::fence_after_sync();
+            if (g.partial) {
+                // split-K: fp32 partial tile of split z (fixed-order reduction afterwards)
+                float* pp = g.partial + (size_t)z * g.M * g.N + row * g.N + n0;
 #pragma unroll 1
+                for (int c0 = 0; c0 < dn::BN; c0 += 32) {
+                    float v[32];
+                    tc::tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)buf * 128u + c0, v);
+                    if (row < g.M && n0 + c0 < g.N) {
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(pp + c0 + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+                    }
+                }
+                tc::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
+                continue;
+            }
+#pragma unroll
             for (int c0 = 0; c0 < dn::BN; c0 += 32) {
                 float v[32];
                 tc::tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)buf * 128u + c0, v);
                 const int64_t col = n0 + c0;
-                if (row < g.M && col < g.N) {          // N is a multiple of 32 on this path (checked by the host)
+                if (row < g.M && col < g.N) {          // N is a multiple of 128 on this path (checked by the host)
                     if (g.bias) {
 #pragma unroll
                         for (int c = 0; c < 32; c += 4) {
@@ -586,12 +626,15 @@ gemm3_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap tmA, const __
                             v[c] += b.x; v[c + 1] += b.y; v[c + 2] += b.z; v[c + 3] += b.w;
                         }
                     }
-                    if (g.residual) {
-                        const float* rp = g.residual + row * g.ldr + col;
+                    if (rrow) {
 #pragma unroll
-                        for (int c = 0; c < 32; c += 4) {
-                            const float4 r = __ldg(reinterpret_cast<const float4*>(rp + c));
-                            v[c] += r.x; v[c + 1] += r.y; v[c + 2] += r.z; v[c + 3] += r.w;
+                        for (int c = 0; c < 8; ++c) {
+                            const float4 r = rr[(c0 / 32) & 1][c];
+                            v[4 * c] += r.x; v[4 * c + 1] += r.y; v[4 * c + 2] += r.z; v[4 * c + 3] += r.w;
+                        }
+                        if (c0 + 64 < dn::BN) {
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) rr[(c0 / 32) & 1][c] = __ldg(reinterpret_cast<const float4*>(rrow + c0 + 64) + c);
                         }
                     }
                     if (g.c_bf16) {
@@ -620,24 +663,25 @@ gemm3_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap tmA, const __
     if (warp == 0) tc::tmem_dealloc(tmem, 256);
 }
 
-// returns GAOT_ERR_UNSUPPORTED when the operands do not meet the TMA constraints (caller falls back to gemm2)
-template <bool B_MN>
-static int launch_gemm3(const GemmArgs& g, cudaStream_t st) {
+// returns GAOT_ERR_UNSUPPORTED when the operands do not meet the TMA constraints (caller falls back to the register-staged kernels)
+template <bool A_MN, bool B_MN>
+static int launch_gemm3(const GemmArgs& g, int splits, cudaStream_t st) {
     static bool attr_done = false;
-    auto kern = gemm3_kernel<B_MN>;
+    auto kern = gemm3_kernel<A_MN, B_MN>;
     if (((uintptr_t)g.A | (uintptr_t)g.B) & 15) return GAOT_ERR_UNSUPPORTED;
     CUtensorMap tmA, tmB;
-    if (!make_tmap(&tmA, g.A, g.M, g.K, g.lda, 128)) return GAOT_ERR_UNSUPPORTED;
-    // B: K-major -> matrix [N, K] (box 128 rows); MN-major -> matrix [K, N] (box 64 contraction rows, two boxes per tile)
+    // K-major operand -> matrix [M or N, K] (box 128 rows x 64 contraction elements);
+    // MN-major operand -> matrix [K, M or N] (box 64 contraction rows x 64 columns, two boxes per tile)
+    if (!(A_MN ? make_tmap(&tmA, g.A, g.K, g.M, g.lda, 64) : make_tmap(&tmA, g.A, g.M, g.K, g.lda, 128))) return GAOT_ERR_UNSUPPORTED;
     if (!(B_MN ? make_tmap(&tmB, g.B, g.K, g.N, g.ldb, 64) : make_tmap(&tmB, g.B, g.N, g.K, g.ldb, 128))) return GAOT_ERR_UNSUPPORTED;
     if (!attr_done) {
         GAOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dn3::SMEM_BYTES));
         attr_done = true;
     }
     const int tiles_n = (int)((g.N + dn::BN - 1) / dn::BN), tiles_m = (int)((g.M + dn::BM - 1) / dn::BM);
-    const int total = tiles_n * tiles_m;
+    const int tiles_mn = tiles_n * tiles_m, total = tiles_mn * splits;
     const int grid = std::min(total, 2 * kNumSMs);
-    kern<<<grid, dn3::THREADS, dn3::SMEM_BYTES, st>>>(g, tmA, tmB, tiles_n, total);
+    kern<<<grid, dn3::THREADS, dn3::SMEM_BYTES, st>>>(g, tmA, tmB, tiles_n, tiles_mn, total);
     GAOT_LAUNCH_CHECK();
     return GAOT_OK;
 }
@@ -716,15 +760,24 @@ static int run_gemm(GemmArgs g, int a_dtype, int b_dtype, bool a_mn, bool b_mn, 
     int rc;
     {   // persistent warp-specialised kernel for bf16 K-major-A products (GAOT_GEMM_OLD=1 selects the one-tile kernel)
         static const bool use_old = getenv("GAOT_GEMM_OLD") && atoi(getenv("GAOT_GEMM_OLD")) != 0;
-        // GAOT_GEMM_GEN=2 pins the register-staged gemm2 (A/B timing); default: the TMA-fed gemm3 when the operands allow it
+        // GAOT_GEMM_GEN=2 pins the register-staged kernels (A/B timing); default: the TMA-fed gemm3 when the operands allow it
         static const bool no_tma = getenv("GAOT_GEMM_GEN") && atoi(getenv("GAOT_GEMM_GEN")) == 2;
-        if (!use_old && a_dtype && b_dtype && !a_mn && !g.A2 && !g.accumulate && splits == 1 && g.N % 32 == 0) {
-            if (!no_tma && g.K % dn::BK == 0 && g.N % dn::BN == 0 && g.M >= dn::BM) {
-                rc = b_mn ? launch_gemm3<true>(g, st) : launch_gemm3<false>(g, st);
-                if (rc != GAOT_ERR_UNSUPPORTED) return rc;
+        const bool tma_ok = !no_tma && !use_old && a_dtype && b_dtype && !g.A2 && !g.accumulate && g.K % dn::BK == 0 &&
+                            g.N % dn::BN == 0 && g.M >= dn::BM && (!a_mn || g.M % dn::BM == 0);
+        if (tma_ok && (!a_mn || b_mn)) {
+            rc = GAOT_ERR_UNSUPPORTED;
+            if (!a_mn && !b_mn && splits == 1) rc = launch_gemm3<false, false>(g, 1, st);
+            else if (!a_mn && b_mn && splits == 1) rc = launch_gemm3<false, true>(g, 1, st);
+            else if (a_mn && b_mn) rc = launch_gemm3<true, true>(g, splits, st);
+            if (rc == GAOT_OK && splits > 1) {
+                const int64_t total4 = g.M * g.N / 4;
+                gemm_splitk_reduce_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(g.partial, splits, g.M, g.N, g.bias, (float*)g.C, g.ldc, g.accumulate);
+                GAOT_LAUNCH_CHECK();
             }
-            return b_mn ? launch_gemm2<true>(g, st) : launch_gemm2<false>(g, st);
+            if (rc != GAOT_ERR_UNSUPPORTED) return rc;
         }
+        if (!use_old && a_dtype && b_dtype && !a_mn && !g.A2 && !g.accumulate && splits == 1 && g.N % 32 == 0)
+            return b_mn ? launch_gemm2<true>(g, st) : launch_gemm2<false>(g, st);
     }
     const int sel = (a_dtype ? 8 : 0) | (b_dtype ? 4 : 0) | (a_mn ? 2 : 0) | (b_mn ? 1 : 0);
     switch (sel) {

@@ -146,9 +146,13 @@ class _BlockFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             dout = dout.to(f32).contiguous().view(M, Hd)
             # ---- FFN: out = h2 + w2(silu(w1 h2) * w3 h2)
-            da = _linear_bwd_x_raw(dout, w2b, BF16)
+            # gradients of the fp32 residual stream feed two GEMMs each as an OPERAND: one bf16 copy (the rounding the
+            # tensor core applies anyway) lets both run on the TMA-fed kernel
+            dout_b = _cast(dout)
+            da = _linear_bwd_x_raw(dout_b, w2b, BF16)
             dw2 = torch.empty(Hd, F, dtype=f32, device=dev)
-            _linear_bwd_w_raw(dout, a, dw2)
+            _linear_bwd_w_raw(dout_b, a, dw2)
+            del dout_b
             dgu = torch.empty(M, 2 * F, dtype=BF16, device=dev)
             check(lib.gaot_swiglu_backward(_p(da), _p(gu), M, F, _p(dgu), _stream(dev)), "swiglu_backward")
             del da
@@ -159,9 +163,11 @@ class _BlockFn(torch.autograd.Function):
             dh, dn2 = _rmsnorm_bwd(dh2, h, rstd2, n2, None)
             del dh2
             # ---- attention: h = x_in + o_proj(attn(norm(x_in)))
-            do = _linear_bwd_x_raw(dh, wob, BF16)
+            dh_b = _cast(dh)
+            do = _linear_bwd_x_raw(dh_b, wob, BF16)
             dwo = torch.empty(Hd, H * d, dtype=f32, device=dev)
-            _linear_bwd_w_raw(dh, o, dwo)
+            _linear_bwd_w_raw(dh_b, o, dwo)
+            del dh_b
             nq, nkv = H * d, Hkv * d
             dqkv = torch.empty(M, nq + 2 * nkv, dtype=BF16, device=dev)
             wsb = lib.gaot_attn_fused_backward_workspace_bytes(B, S, H, d)
