@@ -347,7 +347,7 @@ def main():
                     "share_of_step": kd["share_of_step"]}
     E = wl["n_points"] * wl["k"]
     gno = {}
-    if "gno_fwd" in kernels and "gno_bwd" in kernels:
+    if "gno_fwd" in kernels and "gno_bwd" in kernels and wl.get("strategy", "knn") == "knn":     # E is known only for the knn graphs
         f, b = kernels["gno_fwd"], kernels["gno_bwd"]
         gno = {"edges_per_launch": E, "fwd_edges_per_s": E / (f["avg_launch_ms"] * 1e-3),
                "fwd_bwd_edges_per_s": E / ((f["avg_launch_ms"] + b["avg_launch_ms"]) * 1e-3),

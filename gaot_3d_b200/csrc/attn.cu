@@ -287,6 +287,19 @@ __device__ __forceinline__ void store_row(uint8_t* tile, int row, const uint4 (&
 }
 
 // --------------------------------------------------------------------------- forward
+// 2^x on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], minimax cubic for 2^f
+// (max rel. error 1.0e-4, far below the bf16 rounding of P), n added into the exponent field.  x is clamped at -125
+// (-inf scores of padding keys give 2^-125 ~ 2e-38).  Used for a compile-time fraction of the softmax elements so that the
+// MUFU pipe (16 ex2 / clk / SM: the floor of this kernel at head_dim 32) and the FMA pipe share the exponentials.
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -125.0f);
+    const float t = x + 12582912.0f;                 // 1.5 * 2^23: n lands in the low mantissa bits
+    const float f = x - (t - 12582912.0f);
+    float p = fmaf(f, 0.05500893f, 0.24221096f);
+    p = fmaf(p, f, 0.69328293f);
+    p = fmaf(p, f, 1.0f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -554,7 +567,8 @@ constexpr int NSW = 16;                             // softmax warps
 constexpr int W_MMA = NSW, W_LOAD = NSW + 1, THREADS = (NSW + 2) * 32;
 }
 
-template <bool DROP>
+// EMU = how many of every 32 softmax elements take the polynomial exponential (0, 4, 8, 12)
+template <bool DROP, int EMU>
 __global__ void __launch_bounds__(fw2::THREADS, 1)
 attn_fwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const bf16* __restrict__ Vb,
                  void* __restrict__ out_v, int out_bf16, float* __restrict__ out32, float* __restrict__ lse,
@@ -688,7 +702,10 @@ attn_fwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const
             uint32_t pk[16];
 #pragma unroll
             for (int c = 0; c < 32; c += 2) {
-                float p0 = ex2_approx(sv[c] + nm), p1 = ex2_approx(sv[c + 1] + nm);
+                // pairs picked evenly: pair i is emulated when floor((i+1) k / 16) > floor(i k / 16), k = EMU / 2
+                const bool emu = ((c / 2 + 1) * (EMU / 2)) / 16 > ((c / 2) * (EMU / 2)) / 16;
+                float p0 = emu ? ex2_poly(sv[c] + nm) : ex2_approx(sv[c] + nm);
+                float p1 = emu ? ex2_poly(sv[c + 1] + nm) : ex2_approx(sv[c + 1] + nm);
                 if (DROP) {
                     l_reg += p0 + p1;
                     const uint32_t kk = (uint32_t)(j * 128 + g * 32 + c);
@@ -1401,13 +1418,17 @@ static int attn_launch_fwd(const AttnWs& w, int64_t B, int64_t S, int H, int Hkv
     const char* dbg_env = getenv("GAOT_ATTN_DEBUG");
     const int dbg = dbg_env ? atoi(dbg_env) : 0;
     if (d == 32 && !(dbg & 64)) {                    // warp-specialised kernel (GAOT_ATTN_DEBUG bit 6 selects the older one)
-        if (drop) {
-            GAOT_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fw2::SMEM));
-            attn_fwd2_kernel<true><<<grid, fw2::THREADS, fw2::SMEM, st>>>(w.Qb, w.Kb, w.Vb, out, out_bf16, out32, lse, (int)S, H, Hkv, dc);
-        } else {
-            GAOT_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fw2::SMEM));
-            attn_fwd2_kernel<false><<<grid, fw2::THREADS, fw2::SMEM, st>>>(w.Qb, w.Kb, w.Vb, out, out_bf16, out32, lse, (int)S, H, Hkv, dc);
-        }
+        // GAOT_ATTN_EMU = 0 / 4 / 8 / 12 of every 32 exponentials on the FMA pipe (default: the measured best)
+        static const int emu = getenv("GAOT_ATTN_EMU") ? atoi(getenv("GAOT_ATTN_EMU")) : 4;   // measured at S = 16384: 0.688 / 0.670 / 0.683 / 0.713 ms for 0 / 4 / 8 / 12
+#define GAOT_FWD2(DR, EM)                                                                                              \
+    do { GAOT_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<DR, EM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fw2::SMEM)); \
+         attn_fwd2_kernel<DR, EM><<<grid, fw2::THREADS, fw2::SMEM, st>>>(w.Qb, w.Kb, w.Vb, out, out_bf16, out32, lse, (int)S, H, Hkv, dc); } while (0)
+        if (drop) { if (emu >= 8) GAOT_FWD2(true, 8); else GAOT_FWD2(true, 0); }          // the dropout variant keeps all-MUFU unless asked
+        else if (emu >= 12) GAOT_FWD2(false, 12);
+        else if (emu >= 8) GAOT_FWD2(false, 8);
+        else if (emu >= 4) GAOT_FWD2(false, 4);
+        else GAOT_FWD2(false, 0);
+#undef GAOT_FWD2
         GAOT_LAUNCH_CHECK();
         return GAOT_OK;
     }
