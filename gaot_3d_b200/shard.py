@@ -171,10 +171,11 @@ def sharded_forward(model, batch_local, tokens_pos, n_total: int, group=None, en
 
 
 def allreduce_partial_grads(model, group=None):
-    """GNO-side parameters see only this rank's points -> SUM their grads; the replicated transformer
-    (processor, patch_linear) already holds the total gradient on every rank."""
-    bufs = [p.grad for n, p in model.named_parameters()
-            if p.grad is not None and not (n.startswith("processor.") or n.startswith("patch_linear."))]
+    """GNO-side parameters see only this rank's points -> SUM their grads.  Everything computed on REPLICATED data
+    already holds the total gradient on every rank and is left alone: the transformer (processor, patch_linear) and the
+    encoder's geometric-embedding MLP / recovery layer, which run on the all-reduced latent tokens."""
+    replicated = ("processor.", "patch_linear.", "encoder.geoembed.", "encoder.recovery.")
+    bufs = [p.grad for n, p in model.named_parameters() if p.grad is not None and not n.startswith(replicated)]
     if not bufs:
         return
     flat = torch.cat([b.reshape(-1) for b in bufs])
