@@ -129,7 +129,8 @@ def global_zscore(feat_local: torch.Tensor, n_total: int, group=None) -> torch.T
     return (feat_local - mean.float()) / std
 
 
-def sharded_forward(model, batch_local, tokens_pos, n_total: int, group=None, enc_edges: Optional[torch.Tensor] = None):
+def sharded_forward(model, batch_local, tokens_pos, n_total: int, group=None, enc_edges: Optional[torch.Tensor] = None,
+                    head_parallel: bool = True):
     """GAOT3D forward on this rank's shard of ONE sample (batch of one).  Returns the local rows of
     the output [N_local, C_out].  `model` is a gaot_3d_b200.GAOT3D (single scale, use_gno=True)."""
     enc, dec = model.encoder, model.decoder
@@ -152,7 +153,14 @@ def sharded_forward(model, batch_local, tokens_pos, n_total: int, group=None, en
         # finishes (eigenvalues, z-score over all tokens) identically; coordinates carry no gradient
         geo = enc.geoembed.mlp(sharded_encoder_geo_features(pos, lat, enc_edges, group))
         latent = _apply_node_mlp(enc.recovery, enc.mlp_type, torch.cat([latent, geo], dim=-1))
-    rn = model.process(latent.view(1, M, -1))
+    # the transformer is replicated; its attention core splits by heads across the ranks when the head counts divide
+    # (tblock.set_head_parallel: all-gather of the head outputs forward, of dqkv backward; same kernels, same numbers)
+    from . import tblock
+    tblock.set_head_parallel(head_parallel, group)
+    try:
+        rn = model.process(latent.view(1, M, -1))
+    finally:
+        tblock.set_head_parallel(False)
     rn = all_reduce_backward(rn.reshape(M, -1), group)
     if dec.decoder_strategy == "reverse":            # flip of the *bidirectional* encoder graph (magno.py:263-273)
         bi = enc_edges if enc.encoder_strategy == "bidirectional" else \

@@ -26,6 +26,36 @@ from .ops import _lib_, _p, _stream, _ws, check, _linear_fwd_raw, _linear_bwd_x_
 
 BF16 = torch.bfloat16
 
+# Head-parallel attention for the intra-sample sharded mode (shard.py): the transformer is replicated on every rank, but its
+# attention core -- two thirds of its time at S = 16384 -- splits by heads with no communication before it (q/k/v of a head
+# come from the replicated activations): rank r runs heads [r H/R, (r+1) H/R), the head outputs are all-gathered (8 MB bf16
+# per layer) before the replicated o_proj, and in the backward each rank differentiates its heads and dqkv is all-gathered.
+_HEAD_PARALLEL = {"group": None, "on": False}
+
+
+def set_head_parallel(on: bool, group=None) -> None:
+    _HEAD_PARALLEL["on"], _HEAD_PARALLEL["group"] = bool(on), group
+
+
+def _head_shard(num_heads: int, num_kv_heads: int):
+    if not _HEAD_PARALLEL["on"]:
+        return None
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return None
+    grp = _HEAD_PARALLEL["group"]
+    R = dist.get_world_size(grp)
+    if R == 1 or num_heads % R or num_kv_heads % R:
+        return None
+    return dist.get_rank(grp), R, grp
+
+
+def _gather_cols(local: torch.Tensor, R: int, grp) -> list:
+    import torch.distributed as dist
+    parts = [torch.empty_like(local) for _ in range(R)]
+    dist.all_gather(parts, local.contiguous(), group=grp)
+    return parts
+
 
 def _cast_into(src: torch.Tensor, dst: torch.Tensor) -> None:
     """fp32 parameter -> bf16 operand (dst is a contiguous row slice of the concatenated operand)."""
@@ -86,7 +116,7 @@ class _BlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, skip, cfg, skip_w, skip_b, n1_w, wq, wk, wv, wo, n2_w, w1, w2, w3):
         lib = _lib_()
-        H, Hkv, eps, freqs, p_drop, seed = cfg
+        H, Hkv, eps, freqs, p_drop, seed, hp = cfg
         shape = x.shape
         S, Hd = shape[-2], shape[-1]
         B = x.numel() // (S * Hd)
@@ -109,15 +139,23 @@ class _BlockFn(torch.autograd.Function):
             wqkv = torch.empty(nq + 2 * nkv, Hd, dtype=BF16, device=dev)
             _cast_into(wq, wqkv[:nq]); _cast_into(wk, wqkv[nq:nq + nkv]); _cast_into(wv, wqkv[nq + nkv:])
             qkv = _linear_fwd_raw(h1, None, wqkv, None, None, BF16)
-            packed = torch.empty(lib.gaot_attn_packed_bytes(B, S, H, Hkv, d), dtype=torch.uint8, device=dev)
-            o = torch.empty(M, nq, dtype=BF16, device=dev)
-            o32 = torch.empty(M, nq, dtype=torch.float32, device=dev)        # unrounded copy: the backward's D = rowsum(dO * O)
-            lse = torch.empty(B, H, S, dtype=torch.float32, device=dev)
+            Ha, Hkva = H, Hkv                                                   # heads this rank runs through the attention core
+            if hp is not None:
+                r, R, grp = hp
+                Ha, Hkva = H // R, Hkv // R
+                qkv = torch.cat([qkv[:, r * Ha * d:(r + 1) * Ha * d], qkv[:, nq + r * Hkva * d: nq + (r + 1) * Hkva * d],
+                                 qkv[:, nq + nkv + r * Hkva * d: nq + nkv + (r + 1) * Hkva * d]], dim=1)
+            packed = torch.empty(lib.gaot_attn_packed_bytes(B, S, Ha, Hkva, d), dtype=torch.uint8, device=dev)
+            o = torch.empty(M, Ha * d, dtype=BF16, device=dev)
+            o32 = torch.empty(M, Ha * d, dtype=torch.float32, device=dev)    # unrounded copy: the backward's D = rowsum(dO * O)
+            lse = torch.empty(B, Ha, S, dtype=torch.float32, device=dev)
             fr = None if freqs is None else f32(freqs)
             with ops._timed("attn_fwd", dev):
-                check(lib.gaot_attn_fused_forward(_p(qkv), qkv.stride(0), B, S, H, Hkv, d, _p(fr), float(p_drop), int(seed),
+                check(lib.gaot_attn_fused_forward(_p(qkv), qkv.stride(0), B, S, Ha, Hkva, d, _p(fr), float(p_drop), int(seed),
                                                   _p(packed), _p(o), _p(o32), _p(lse), _stream(dev)), "attn_fused_forward")
             del qkv
+            if hp is not None:
+                o = torch.cat(_gather_cols(o, hp[1], hp[2]), dim=1)            # [M, H*d]: every rank's heads, in head order
             wob = _cast(wo)
             h = _linear_fwd_raw(o, None, wob, None, x_in)                       # x + attn(norm(x))
             h2b, h2, rstd2 = _rmsnorm_fwd(h, n2, eps, True)
@@ -132,13 +170,13 @@ class _BlockFn(torch.autograd.Function):
         ctx.save_for_backward(x2d, s2d, x_in, rstd1, h1, packed, o, o32, lse, h, rstd2, h2b, gu, a,
                               wsk, wqkv, wob, w13, w2b, n1, n2, fr)
         ctx.meta = (shape, None if skip is None else skip.shape, B, S, Hd, H, Hkv, d, F, float(p_drop), int(seed),
-                    skip_b is not None)
+                    skip_b is not None, hp)
         return out.view(shape)
 
     @staticmethod
     def backward(ctx, dout):
         (x2d, s2d, x_in, rstd1, h1, packed, o, o32, lse, h, rstd2, h2b, gu, a, wsk, wqkv, wob, w13, w2b, n1, n2, fr) = ctx.saved_tensors
-        shape, skip_shape, B, S, Hd, H, Hkv, d, F, p_drop, seed, has_skip_bias = ctx.meta
+        shape, skip_shape, B, S, Hd, H, Hkv, d, F, p_drop, seed, has_skip_bias, hp = ctx.meta
         lib = _lib_()
         M = B * S
         dev = dout.device
@@ -169,13 +207,23 @@ class _BlockFn(torch.autograd.Function):
             _linear_bwd_w_raw(dh_b, o, dwo)
             del dh_b
             nq, nkv = H * d, Hkv * d
-            dqkv = torch.empty(M, nq + 2 * nkv, dtype=BF16, device=dev)
-            wsb = lib.gaot_attn_fused_backward_workspace_bytes(B, S, H, d)
+            Ha, Hkva = H, Hkv
+            if hp is not None:
+                r, R, grp = hp
+                Ha, Hkva = H // R, Hkv // R
+                do = do[:, r * Ha * d:(r + 1) * Ha * d].contiguous()
+            dqkv = torch.empty(M, (Ha + 2 * Hkva) * d, dtype=BF16, device=dev)
+            wsb = lib.gaot_attn_fused_backward_workspace_bytes(B, S, Ha, d)
             ws = _ws(wsb, dev)
             with ops._timed("attn_bwd", dev):
-                check(lib.gaot_attn_fused_backward(_p(packed), _p(o32), _p(do), _p(lse), B, S, H, Hkv, d, _p(fr), p_drop, seed,
+                check(lib.gaot_attn_fused_backward(_p(packed), _p(o32), _p(do), _p(lse), B, S, Ha, Hkva, d, _p(fr), p_drop, seed,
                                                    _p(ws), wsb, _p(dqkv), dqkv.stride(0), _stream(dev)), "attn_fused_backward")
             del do, ws
+            if hp is not None:                                                  # [dq_l | dk_l | dv_l] of every rank -> [dq | dk | dv]
+                parts = _gather_cols(dqkv, hp[1], hp[2])
+                qa, ka = Ha * d, Hkva * d
+                dqkv = torch.cat([p_[:, :qa] for p_ in parts] + [p_[:, qa:qa + ka] for p_ in parts] +
+                                 [p_[:, qa + ka:] for p_ in parts], dim=1)
             dh1 = _linear_bwd_x_raw(dqkv, wqkv, f32)
             dwqkv = torch.empty(nq + 2 * nkv, Hd, dtype=f32, device=dev)
             _linear_bwd_w_raw(dqkv, h1, dwqkv)
@@ -206,5 +254,6 @@ def transformer_block(x, skip, *, num_heads: int, num_kv_heads: int, eps: float,
     ops._need_cuda(x, skip)
     if dropout_p > 0.0 and seed is None:
         seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-    cfg = (int(num_heads), int(num_kv_heads), float(eps), rope_freqs, float(dropout_p), int(seed or 0))
+    cfg = (int(num_heads), int(num_kv_heads), float(eps), rope_freqs, float(dropout_p), int(seed or 0),
+           _head_shard(int(num_heads), int(num_kv_heads)))
     return _BlockFn.apply(x, skip, cfg, skip_w, skip_b, attn_norm_w, wq, wk, wv, wo, ffn_norm_w, w1, w2, w3)
