@@ -162,8 +162,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gno-precision", default="bf16", choices=["fp32", "bf16"],
                     help="per-edge kernel MLP operands: bf16 tcgen05 (rtol 2e-2 tier of the north star, default) or fp32 CUDA cores (rtol 1e-5 tier)")
-    ap.add_argument("--node-mlp", default="tf32", choices=["fp32", "tf32"],
-                    help="node-level torch GEMMs (lifting / projection / recovery): TF32 tensor cores (what the reference's default Conv1d node MLPs get from cuDNN) or strict fp32")
+    ap.add_argument("--node-mlp", default="fused", choices=["fp32", "tf32", "fused"],
+                    help="node-level MLPs (lifting / projection / recovery): strict fp32 torch GEMMs, TF32 torch GEMMs (what the reference's "
+                         "default Conv1d node MLPs get from cuDNN), or TF32 + the fused f16/bf16 tensor-core kernel for the projection head")
     ap.add_argument("--shard", action="store_true", help="intra-sample sharding: all ranks cooperate on ONE sample (strong scaling)")
     ap.add_argument("--profile-step", action="store_true", help="warm up, then run ONE step between cudaProfilerStart/Stop (for ncu --profile-from-start off) and exit")
     args = ap.parse_args()
@@ -222,7 +223,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     G.set_gno_precision(args.gno_precision)
-    G.set_node_mlp_tf32(args.node_mlp == "tf32")
+    G.set_node_mlp_mode({"fp32": "torch", "tf32": "tf32", "fused": "fused"}[args.node_mlp])
     torch.manual_seed(0)
     mc = G.MAGNOConfig(gno_coord_dim=3, lifting_channels=C_LIFT, neighbor_strategy=wl.get("strategy", "knn"), k_neighbors=wl["k"],
                        gno_radius=wl.get("radius", 0.033),

@@ -47,6 +47,10 @@ _SIGS = {
     "gaot_geo_moments": (c_int, [P, c_int64, P, c_int64, P, P, P, P]),
     "gaot_geo_from_moments": (c_int, [P, c_int64, P, P]),
     "gaot_geo_zscore_workspace_bytes": (c_size_t, [c_int64]),
+    "gaot_node_mlp2_supported": (c_int, [c_int32, c_int32, c_int32]),
+    "gaot_node_mlp2_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
+    "gaot_node_mlp2_forward": (c_int, [P, c_int64, c_int32, c_int32, c_int32, P, P, P, P, P, P]),
+    "gaot_node_mlp2_backward": (c_int, [P, P, c_int64, c_int32, c_int32, c_int32, P, P, P, P, c_size_t, P, P, P]),
     "gaot_geo_zscore": (c_int, [P, c_int64, c_int32, P, c_size_t, P]),
     "gaot_attn_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32, c_int32, c_int32]),
     "gaot_attn_forward": (c_int, [P, P, P, c_int64, c_int64, c_int32, c_int32, c_int32, P, c_float, c_uint64, P, c_size_t, P, P, P]),

@@ -12,6 +12,9 @@ from typing import Any, Optional
 import torch
 import torch.nn as nn
 
+from .. import ops
+import torch.nn.functional as F
+
 from .geoembed import GeometricEmbedding
 from .integral_transform import IntegralTransform
 from .mlp import ChannelMLP, LinearChannelMLP
@@ -62,6 +65,15 @@ def _node_mlp(mlp_type, cin, cout, hidden=None):
 
 
 def _apply_node_mlp(mlp, mlp_type, x):
+    # two-layer GELU MLPs of the projection-head shape run as ONE fused tensor-core kernel when the process opted into the
+    # mixed-precision tier (ops.set_node_mlp_mode("fused")); Linear and kernel-size-1 Conv1d hold the same [out, in] matrices
+    if ops.node_mlp_mode() == "fused" and x.is_cuda and getattr(mlp, "n_layers", 0) == 2 and mlp.dropout is None \
+            and mlp.non_linearity is F.gelu:
+        w1, w2 = mlp.fcs[0].weight, mlp.fcs[1].weight
+        w1, w2 = w1.reshape(w1.shape[0], -1), w2.reshape(w2.shape[0], -1)
+        if mlp.fcs[0].bias is not None and mlp.fcs[1].bias is not None and x.dim() == 2 and \
+                ops.node_mlp2_supported(w1.shape[1], w1.shape[0], w2.shape[0]):
+            return ops.node_mlp2(x, w1, mlp.fcs[0].bias, w2, mlp.fcs[1].bias)
     return mlp(x) if mlp_type == "linear" else mlp(x.transpose(0, 1)).transpose(0, 1)
 
 

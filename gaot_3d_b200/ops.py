@@ -28,6 +28,24 @@ def get_gno_precision() -> str:
     return "fp32" if _PRECISION["gno"] == 0 else "bf16"
 
 
+_NODE_MLP = {"mode": "torch"}
+
+
+def set_node_mlp_mode(mode: str) -> None:
+    """'torch' (default: torch GEMMs in whatever precision torch's flags say), 'tf32' (torch GEMMs with the TF32 flags
+    on), or 'fused' (TF32 flags on, and two-layer GELU MLPs of the projection-head shape 32 -> 256 -> <= 8 as one fused
+    tensor-core kernel with f16/bf16 operands -- the rtol 2e-2 tier)."""
+    if mode not in ("torch", "tf32", "fused"):
+        raise ValueError("node MLP mode must be 'torch', 'tf32' or 'fused'")
+    _NODE_MLP["mode"] = mode
+    if mode != "torch":
+        set_node_mlp_tf32(True)
+
+
+def node_mlp_mode() -> str:
+    return _NODE_MLP["mode"]
+
+
 def set_node_mlp_tf32(on: bool = True) -> None:
     """Node-level MLPs (lifting, projection, recovery, geo-embedding MLP) are torch fp32 GEMMs on [N_points, C]
     tensors.  The reference's default mlp_type='channel' routes them through Conv1d, for which cuDNN allows TF32
@@ -382,6 +400,56 @@ def zscore_(feat: torch.Tensor) -> torch.Tensor:
     with torch.cuda.device(dev):
         check(lib.gaot_geo_zscore(_p(feat), feat.shape[0], feat.shape[1], _p(ws), wsb, _stream(dev)), "geo_zscore")
     return feat
+
+
+# ----------------------------------------------------------------------------- fused two-layer node MLP
+def node_mlp2_supported(c_in: int, hidden: int, c_out: int) -> bool:
+    return bool(_lib_().gaot_node_mlp2_supported(int(c_in), int(hidden), int(c_out)))
+
+
+class _NodeMlp2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        lib = _lib_()
+        f32 = lambda t: t.detach().to(torch.float32).contiguous()
+        xd, w1d, b1d, w2d, b2d = f32(x), f32(w1), f32(b1), f32(w2), f32(b2)
+        n, c_in = xd.shape
+        hidden, c_out = w1d.shape[0], w2d.shape[0]
+        dev = xd.device
+        y = torch.empty(n, c_out, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.gaot_node_mlp2_forward(_p(xd), n, c_in, hidden, c_out, _p(w1d), _p(b1d), _p(w2d), _p(b2d), _p(y),
+                                             _stream(dev)), "node_mlp2_forward")
+        ctx.save_for_backward(xd, w1d, b1d, w2d)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xd, w1d, b1d, w2d = ctx.saved_tensors
+        lib = _lib_()
+        n, c_in = xd.shape
+        hidden, c_out = w1d.shape[0], w2d.shape[0]
+        dev = xd.device
+        dy = dy.to(torch.float32).contiguous()
+        dx = torch.empty_like(xd) if ctx.needs_input_grad[0] else None
+        dpar = torch.empty(hidden * c_in + hidden + c_out * hidden + c_out, dtype=torch.float32, device=dev)
+        wsb = lib.gaot_node_mlp2_workspace_bytes(c_in, hidden, c_out)
+        ws = _ws(wsb, dev)
+        with torch.cuda.device(dev):
+            check(lib.gaot_node_mlp2_backward(_p(xd), _p(dy), n, c_in, hidden, c_out, _p(w1d), _p(b1d), _p(w2d), _p(ws), wsb,
+                                              _p(dx), _p(dpar), _stream(dev)), "node_mlp2_backward")
+        o1, o2, o3 = hidden * c_in, hidden * c_in + hidden, hidden * c_in + hidden + c_out * hidden
+        return dx, dpar[:o1].view(hidden, c_in), dpar[o1:o2], dpar[o2:o3].view(c_out, hidden), dpar[o3:]
+
+
+def node_mlp2(x, w1, b1, w2, b2):
+    """y = W2 gelu(W1 x + b1) + b2 on [N, 32] rows as one fused tensor-core kernel (forward) and one more (backward):
+    the projection head of the decoder (reference magno.py:640-644, :796-797).  Gradients flow to x and all four
+    parameters; weight shapes [hidden, c_in] / [c_out, hidden] (a kernel-size-1 Conv1d weight reshaped is the same)."""
+    _need_cuda(x, w1, b1, w2, b2)
+    w1_, w2_ = w1.reshape(w1.shape[0], -1), w2.reshape(w2.shape[0], -1)
+    y = _NodeMlp2Fn.apply(x, w1_, b1, w2_, b2)
+    return y
 
 
 # ----------------------------------------------------------------------------- dense layers (nn.Linear)

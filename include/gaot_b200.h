@@ -154,6 +154,22 @@ int gaot_geo_from_moments(const float* moments, int64_t nq, float* feat, void* s
 size_t gaot_geo_zscore_workspace_bytes(int64_t nq);
 int gaot_geo_zscore(float* feat, int64_t nq, int32_t nfeat, void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------ fused two-layer node MLP
+ * y = W2 gelu(W1 x + b1) + b2 on every row of x [n, c_in]: the decoder's projection head
+ *   (reference src/model/layers/magno.py:640-644 `self.projection`, applied at :796-797; LinearChannelMLP / ChannelMLP
+ *   forward mlp.py:327-335, :283-305).  W1 [hidden, c_in], W2 [c_out, hidden] row-major fp32 (a kernel-size-1 Conv1d
+ *   weight has the same layout).  f16/bf16 tensor-core operands, fp32 accumulation, tanh-form GELU (rtol 2e-2 tier).
+ * Envelope: c_in = 32, hidden = 256, c_out <= 8 (gaot_node_mlp2_supported); outside it the entry points return
+ * GAOT_ERR_UNSUPPORTED and the caller keeps its library GEMMs.
+ * backward: d_params = [dW1 (hidden x c_in) | db1 (hidden) | dW2 (c_out x hidden) | db2 (c_out)]; d_x may be null. */
+int gaot_node_mlp2_supported(int32_t c_in, int32_t hidden, int32_t c_out);
+size_t gaot_node_mlp2_workspace_bytes(int32_t c_in, int32_t hidden, int32_t c_out);
+int gaot_node_mlp2_forward(const float* x, int64_t n, int32_t c_in, int32_t hidden, int32_t c_out, const float* w1,
+                           const float* b1, const float* w2, const float* b2, float* y, void* stream);
+int gaot_node_mlp2_backward(const float* x, const float* d_y, int64_t n, int32_t c_in, int32_t hidden, int32_t c_out,
+                            const float* w1, const float* b1, const float* w2, void* ws, size_t ws_bytes, float* d_x,
+                            float* d_params, void* stream);
+
 /* ------------------------------------------------------------------ latent attention
  * Replaces rotary_emb + F.scaled_dot_product_attention of reference
  *   src/model/layers/attn.py:110-128.  q [B,S,H*d], k,v [B,S,Hkv*d] float32 (projection
