@@ -11,6 +11,7 @@
 // HBM-bound integer/byte work: coalesced 16-byte source records, int32 internals, int64
 // only at the edge_index boundary.
 #include "common.cuh"
+#include <cstdlib>
 #include "graph_core.cuh"
 
 namespace gaot {
@@ -131,6 +132,80 @@ radius_emit_kernel(const float* __restrict__ y, int64_t ny, const int32_t* __res
     for (int j = 0; j < n; ++j) {
         out_y[beg + j] = q;
         out_x[beg + j] = list[j];
+    }
+}
+
+// ---- warp-per-query radius search: the encoder side (queries = latent tokens, sources = the physical cloud) has
+// hundreds to thousands of candidates per query (582 at 500 K points, ~9 000 at 8 M) and few queries: one thread per query
+// is a long serial scan on a fraction of the SMs.  Here the 32 lanes stride over the candidates of every cell column
+// (coalesced 16-byte SrcPoint loads); COUNT is a warp sum; EMIT keeps the `cap` smallest matching source indices
+// as a sorted list distributed over the lanes (lane i = i-th smallest) and inserts the rare improving candidates with one
+// shuffle each (expected ~ cap (1 + ln(m / cap)) insertions for m matches).  Same result as radius_query<true>: the
+// first `cap` matches by ascending source index, in ascending order (torch_cluster's CUDA semantics).  cap <= 32.
+template <bool EMIT>
+__global__ void __launch_bounds__(128)
+radius_warp_kernel(const float* __restrict__ y, int64_t ny, const int32_t* __restrict__ qperm,
+                   const GridParams* __restrict__ gp, const int32_t* __restrict__ cell_start,
+                   const SrcPoint* __restrict__ pts, float r2, int cap, int32_t* __restrict__ counts,
+                   const int32_t* __restrict__ rowptr, int64_t* __restrict__ out_y, int64_t* __restrict__ out_x) {
+    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (t >= ny) return;
+    const GridParams g = *gp;
+    const int q = qperm[t];
+    int obeg = 0, nout = 0;
+    if (EMIT) {
+        obeg = rowptr[q];
+        nout = rowptr[q + 1] - obeg;
+        if (nout == 0) return;
+    }
+    const float qx = y[(int64_t)q * 3], qy = y[(int64_t)q * 3 + 1], qz = y[(int64_t)q * 3 + 2];
+    const int cx = cell_coord(qx, g.ox, g.inv_h, g.nx), cy = cell_coord(qy, g.oy, g.inv_h, g.ny), cz = cell_coord(qz, g.oz, g.inv_h, g.nz);
+    const int R = g.reach;
+    const int x0 = clampi(cx - R, 0, g.nx - 1), x1 = clampi(cx + R, 0, g.nx - 1);
+    const int y0 = clampi(cy - R, 0, g.ny - 1), y1 = clampi(cy + R, 0, g.ny - 1);
+    const int z0 = clampi(cz - R, 0, g.nz - 1), z1 = clampi(cz + R, 0, g.nz - 1);
+    int n = 0;
+    int best = 0x7fffffff;                       // EMIT: lane i holds the i-th smallest matching index so far
+    for (int ix = x0; ix <= x1; ++ix) {
+        for (int iy = y0; iy <= y1; ++iy) {
+            const int beg = cell_start[cell_id(g, ix, iy, z0)];
+            const int end = cell_start[cell_id(g, ix, iy, z1) + 1];
+            for (int base = beg; base < end; base += 32) {
+                const int p = base + lane;
+                bool match = false;
+                int idx = 0;
+                if (p < end) {
+                    const SrcPoint s = pts[p];
+                    match = dist2(s.x, s.y, s.z, qx, qy, qz) < r2;
+                    idx = s.idx;
+                }
+                if (!EMIT) {
+                    n += match ? 1 : 0;
+                } else {
+                    int thr = __shfl_sync(0xffffffffu, best, cap - 1);
+                    unsigned mask = __ballot_sync(0xffffffffu, match && idx < thr);
+                    while (mask) {
+                        const int sl = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const int v = __shfl_sync(0xffffffffu, idx, sl);
+                        if (v >= thr) continue;                          // the threshold tightened since the ballot
+                        int up = __shfl_up_sync(0xffffffffu, best, 1);
+                        if (lane == 0) up = (int)0x80000000;
+                        if (best > v) best = max(v, up);
+                        thr = __shfl_sync(0xffffffffu, best, cap - 1);
+                    }
+                }
+            }
+        }
+    }
+    if (!EMIT) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+        if (lane == 0) counts[q] = n > cap ? cap : n;
+    } else if (lane < nout) {
+        out_y[obeg + lane] = q;
+        out_x[obeg + lane] = best;
     }
 }
 
@@ -314,6 +389,14 @@ static inline int bits_for(int64_t maxval) { int b = 1; while (((int64_t)1 << b)
 using namespace gaot;
 
 // ================================================================ C ABI
+// sources denser than queries (the encoder direction): one warp per query; GAOT_RADIUS_WARP=0/1 forces the choice
+static bool radius_use_warp(int64_t nx, int64_t ny, int cap) {
+    static const char* e = getenv("GAOT_RADIUS_WARP");
+    if (cap > 32) return false;
+    if (e) return atoi(e) != 0;
+    return nx >= 2 * ny;
+}
+
 extern "C" {
 
 size_t gaot_radius_workspace_bytes(int64_t nx, int64_t ny) { return cell_ws_bytes(nx, ny); }
@@ -333,8 +416,12 @@ int gaot_radius_count(const float* x, int64_t nx, const float* y, int64_t ny, do
     if (!carve(w, ws, ws_bytes, nx, ny)) { set_error("radius: workspace too small"); return GAOT_ERR_WORKSPACE; }
     int rc = build_cells(x, nx, y, ny, (float)r, 0, w, st);
     if (rc) return rc;
-    radius_count_kernel<32><<<nblk(ny, 128), 128, 0, st>>>(y, ny, w.qperm, w.gp, w.cell_start, w.pts,
-                                                          r2_of(r), cap, w.counts);
+    if (radius_use_warp(nx, ny, cap))
+        radius_warp_kernel<false><<<nblk(ny * 32, 128), 128, 0, st>>>(y, ny, w.qperm, w.gp, w.cell_start, w.pts, r2_of(r), cap,
+                                                                       w.counts, nullptr, nullptr, nullptr);
+    else
+        radius_count_kernel<32><<<nblk(ny, 128), 128, 0, st>>>(y, ny, w.qperm, w.gp, w.cell_start, w.pts,
+                                                              r2_of(r), cap, w.counts);
     GAOT_LAUNCH_CHECK();
     rc = exclusive_scan_i32(w.counts, rowptr, ny, true, w.scan_ws, w.scan_bytes, st);
     if (rc) return rc;
@@ -355,7 +442,10 @@ int gaot_radius_emit(const float* x, int64_t nx, const float* y, int64_t ny, dou
     if (nx == 0 || ny == 0) return GAOT_OK;
     CellWs w;
     if (!carve(w, ws, ws_bytes, nx, ny)) { set_error("radius: workspace too small"); return GAOT_ERR_WORKSPACE; }
-    if (cap <= 32)
+    if (radius_use_warp(nx, ny, cap))
+        radius_warp_kernel<true><<<nblk(ny * 32, 128), 128, 0, st>>>(y, ny, w.qperm, w.gp, w.cell_start, w.pts, r2_of(r), cap,
+                                                                      nullptr, rowptr, out_y, out_x);
+    else if (cap <= 32)
         radius_emit_kernel<32><<<nblk(ny, 128), 128, 0, st>>>(y, ny, w.qperm, w.gp, w.cell_start, w.pts,
                                                              r2_of(r), cap, rowptr, out_y, out_x);
     else

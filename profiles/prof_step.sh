@@ -3,7 +3,7 @@ set -x
 mkdir -p gpurun_out
 B="python bench.py --profile-step --no-cpu-baseline"
 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv $B > gpurun_out/l.log 2>&1
-for k in attn_bwd2_kernel attn_fwd2_kernel gemm2_kernel gno_fwd_tc2_kernel gno_bwd_tc2_kernel knn_kernel; do
+for k in attn_bwd2_kernel attn_fwd2_kernel gemm3_kernel gno_fwd_tc2_kernel gno_bwd_tc2_kernel node_mlp2_bwd_kernel knn_kernel; do
   timeout 300 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:$k -c 1 -f -o gpurun_out/prof_$k $B > gpurun_out/p_$k.log 2>&1
 done
 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_default.json 2> gpurun_out/b.err

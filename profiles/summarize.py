@@ -52,7 +52,7 @@ for rep in sorted(glob.glob(os.path.join(src, "prof_*.ncu-rep"))):
 # DRAM traffic per launch of each captured kernel -> profiles/traffic.json (read by bench.py's roofline.traffic)
 import json
 alias = {"attn_bwd2_kernel": "attn_bwd", "attn_bwd_kernel": "attn_bwd", "attn_fwd_kernel": "attn_fwd", "attn_fwd2_kernel": "attn_fwd",
-         "gno_fwd_tc_kernel": "gno_fwd", "gno_bwd_tc_kernel": "gno_bwd", "gno_fwd_tc2_kernel": "gno_fwd", "gno_bwd_tc2_kernel": "gno_bwd", "gemm_tc_kernel": "linear_bwd_w", "gemm2_kernel": "linear_fwd", "knn_kernel": "knn_search"}
+         "gno_fwd_tc_kernel": "gno_fwd", "gno_bwd_tc_kernel": "gno_bwd", "gno_fwd_tc2_kernel": "gno_fwd", "gno_bwd_tc2_kernel": "gno_bwd", "gemm_tc_kernel": "linear_bwd_w", "gemm2_kernel": "linear_fwd", "gemm3_kernel": "linear_fwd", "node_mlp2_bwd_kernel": "node_mlp_bwd", "node_mlp2_fwd_kernel": "node_mlp_fwd", "knn_kernel": "knn_search"}
 tp = "profiles/traffic.json"
 traffic = json.load(open(tp)) if os.path.exists(tp) else {}
 for rep in sorted(glob.glob(os.path.join(src, "prof_*.ncu-rep"))):
