@@ -1,8 +1,9 @@
-"""Geometric embedding -- drop-in for reference src/model/layers/geoembed.py ('statistical' method).
+"""Geometric embedding -- drop-in for reference src/model/layers/geoembed.py ('statistical' and 'pointnet').
 
-Parameter names match (`mlp.0`, `mlp.2`).  The per-query statistics (count, mean/var of distance,
-centroid offset, covariance eigenvalues) and the global z-score are CUDA kernels (geo.cu); the
-9->64->out MLP on [N_q, 9] stays a torch GEMM.
+Parameter names match (`mlp.0`, `mlp.2`; `pointnet_mlp.0`, `pointnet_mlp.2`, `fc.0`).  'statistical': the per-query
+statistics (count, mean/var of distance, centroid offset, covariance eigenvalues) and the global z-score are CUDA
+kernels (geo.cu); the 9->64->out MLP on [N_q, 9] stays a torch GEMM.  'pointnet': the per-edge 3->32->32 ReLU MLP and
+the max / mean pool over each query's edges are one CUDA kernel (pointnet.cu); the Linear(32->out) behind it is torch.
 """
 from typing import Optional
 
@@ -21,9 +22,9 @@ class GeometricEmbedding(nn.Module):
             raise ValueError(f"Unsupported pooling method: {self.pooling}. Supported methods: 'max', 'mean'.")
         if self.method == "statistical":
             self.mlp = nn.Sequential(nn.Linear(self._get_stat_feature_dim(), 64), nn.ReLU(), nn.Linear(64, output_dim))
-        elif self.method == "pointnet":
-            # SURVEY.md §8(f) rank 3
-            raise NotImplementedError("'pointnet' geometric embedding is not built yet (statistical only)")
+        elif self.method == "pointnet":                      # reference geoembed.py:42-53
+            self.pointnet_mlp = nn.Sequential(nn.Linear(input_dim, 32), nn.ReLU(), nn.Linear(32, 32), nn.ReLU())
+            self.fc = nn.Sequential(nn.Linear(32, output_dim))
         else:
             raise ValueError(f"Unknown method: {self.method}")
 
@@ -43,5 +44,18 @@ class GeometricEmbedding(nn.Module):
         if neighbors_counts is not None:
             raise NotImplementedError("neighbors_counts override is unused by the reference (magno.py:513-516)")
         if self.input_dim == 2:
-            raise NotImplementedError("2-D statistical embedding needs the z-score on the reduced feature set")
+            raise NotImplementedError("2-D geometric embedding: the kernels are built for 3-D coordinates")
+        if self.method == "pointnet":
+            return self.pointnet_features(source_pos, query_pos, edge_index)
         return self.mlp(self.statistical_features(source_pos, query_pos, edge_index))
+
+    def pointnet_features(self, source_pos, query_pos, edge_index):
+        """Reference geoembed.py:184-222: pooled per-edge MLP features -> fc; rows of queries without neighbours are 0."""
+        nq = query_pos.shape[0]
+        if edge_index.numel() == 0:
+            return torch.zeros(nq, self.output_dim, device=query_pos.device, dtype=query_pos.dtype)
+        csr = ops.csr_of(edge_index, source_pos.shape[0], nq)
+        l1, l2 = self.pointnet_mlp[0], self.pointnet_mlp[2]
+        pooled = ops.pointnet_pool(source_pos, query_pos, csr, l1.weight, l1.bias, l2.weight, l2.bias, self.pooling)
+        has = (csr.rowptr[1:] > csr.rowptr[:-1]).to(pooled.dtype).unsqueeze(1)
+        return self.fc(pooled) * has

@@ -391,6 +391,46 @@ def geo_from_moments(moments: torch.Tensor, normalize: bool = True) -> torch.Ten
     return feat
 
 
+class _PointNetPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sp, qp, csr, pooling, w1, b1, w2, b2):
+        lib = _lib_()
+        dev = qp.device
+        params = torch.cat([w1.reshape(-1), b1.reshape(-1), w2.reshape(-1), b2.reshape(-1)]).detach().to(torch.float32).contiguous()
+        pooled = torch.empty(csr.nq, 32, dtype=torch.float32, device=dev)
+        argmax = torch.empty(csr.nq, 32, dtype=torch.int32, device=dev) if pooling == 0 else None
+        with torch.cuda.device(dev):
+            check(lib.gaot_pointnet_forward(_p(sp), csr.n_src, _p(qp), csr.nq, _p(csr.rowptr), _p(csr.src), _p(params), pooling,
+                                            _p(pooled), _p(argmax), _stream(dev)), "pointnet_forward")
+        ctx.save_for_backward(sp, qp, params, argmax)
+        ctx.csr, ctx.pooling = csr, pooling
+        return pooled
+
+    @staticmethod
+    def backward(ctx, d_pooled):
+        sp, qp, params, argmax = ctx.saved_tensors
+        csr = ctx.csr
+        lib = _lib_()
+        dev = qp.device
+        d_pooled = d_pooled.to(torch.float32).contiguous()
+        dpar = torch.empty_like(params)
+        wsb = lib.gaot_pointnet_workspace_bytes()
+        ws = _ws(wsb, dev)
+        with torch.cuda.device(dev):
+            check(lib.gaot_pointnet_backward(_p(sp), csr.n_src, _p(qp), csr.nq, _p(csr.rowptr), _p(csr.src), _p(params), ctx.pooling,
+                                             _p(d_pooled), _p(argmax), _p(ws), wsb, _p(dpar), _stream(dev)), "pointnet_backward")
+        return None, None, None, None, dpar[:96].view(32, 3), dpar[96:128], dpar[128:1152].view(32, 32), dpar[1152:]
+
+
+def pointnet_pool(source_pos, query_pos, csr: Csr, w1, b1, w2, b2, pooling: str = "max") -> torch.Tensor:
+    """[nq, 32] pooled PointNet features of the centred neighbour coordinates (reference geoembed.py:184-213):
+    relu(W2 relu(W1 (y - x) + b1) + b2) per edge, max or mean over each query's edges, 0 for empty queries."""
+    _need_cuda(source_pos, query_pos, w1)
+    if tuple(w1.shape) != (32, 3) or tuple(w2.shape) != (32, 32):
+        raise NotImplementedError("pointnet_pool: the fused kernel is built for the reference's 3 -> 32 -> 32 MLP")
+    return _PointNetPoolFn.apply(_pos3(source_pos), _pos3(query_pos), csr, 0 if pooling == "max" else 1, w1, b1, w2, b2)
+
+
 def zscore_(feat: torch.Tensor) -> torch.Tensor:
     _need_cuda(feat)
     lib = _lib_()

@@ -154,6 +154,19 @@ int gaot_geo_from_moments(const float* moments, int64_t nq, float* feat, void* s
 size_t gaot_geo_zscore_workspace_bytes(int64_t nq);
 int gaot_geo_zscore(float* feat, int64_t nq, int32_t nfeat, void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------ PointNet-style geometric embedding (pooling part)
+ * Replaces the gathers + per-edge `pointnet_mlp` + scatter(max|mean) of reference src/model/layers/geoembed.py:184-213
+ * (method='pointnet'): pooled[q, 0..31] = pool_e relu(W2 relu(W1 (y[src(e)] - x[q]) + b1) + b2) over the CSR row of q,
+ * 0 for an empty query.  params = [W1 (32 x 3) | b1 (32) | W2 (32 x 32) | b2 (32)] fp32; pooling 0 = max, 1 = mean.
+ * `argmax` [nq, 32] int32 (max pooling: CSR position of the first maximal edge per channel, -1 if none) is written by the
+ * forward and read by the backward.  Backward: parameter gradients only (coordinates carry none), same layout as params. */
+size_t gaot_pointnet_workspace_bytes(void);
+int gaot_pointnet_forward(const float* src_pos, int64_t n_src, const float* qry_pos, int64_t nq, const int32_t* rowptr,
+                          const int32_t* csr_src, const float* params, int pooling, float* pooled, int32_t* argmax, void* stream);
+int gaot_pointnet_backward(const float* src_pos, int64_t n_src, const float* qry_pos, int64_t nq, const int32_t* rowptr,
+                           const int32_t* csr_src, const float* params, int pooling, const float* d_pooled, const int32_t* argmax,
+                           void* ws, size_t ws_bytes, float* d_params, void* stream);
+
 /* ------------------------------------------------------------------ fused two-layer node MLP
  * y = W2 gelu(W1 x + b1) + b2 on every row of x [n, c_in]: the decoder's projection head
  *   (reference src/model/layers/magno.py:640-644 `self.projection`, applied at :796-797; LinearChannelMLP / ChannelMLP

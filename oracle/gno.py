@@ -89,6 +89,26 @@ def geo_statistical_features(source_pos, query_pos, edge_index, normalize=True):
     return (feat - mean) / std
 
 
+def geo_pointnet_embedding(source_pos, query_pos, edge_index, w1, b1, w2, b2, wf, bf, pooling="max"):
+    """GeometricEmbedding._compute_pointnet_features_pyg, reference geoembed.py:184-222: per-edge
+    relu(Linear(relu(Linear(y - x)))) (:206), scatter max | mean with a zero-initialised output (:208-213, the native
+    scatter's amax with include_self=False keeps 0 for empty queries), fc (:215), rows without neighbours zeroed (:216)."""
+    nq = query_pos.shape[0]
+    out_dim = wf.shape[0]
+    out = torch.zeros(nq, out_dim, dtype=query_pos.dtype)
+    if edge_index.numel() == 0:
+        return out
+    src, qry = edge_index[0].long(), edge_index[1].long()
+    has = torch.bincount(qry, minlength=nq) > 0
+    h = F.relu(F.linear(F.relu(F.linear(source_pos[src] - query_pos[qry], w1, b1)), w2, b2))
+    if pooling == "max":
+        pooled = torch.zeros(nq, h.shape[1], dtype=h.dtype).scatter_reduce(0, qry[:, None].expand_as(h), h, reduce="amax", include_self=False)
+    else:
+        pooled = scatter_mean(h, qry, nq)
+    res = F.linear(pooled, wf, bf)
+    return torch.where(has[:, None], res, out)
+
+
 def geo_embedding(source_pos, query_pos, edge_index, w0, b0, w1, b1):
     """GeometricEmbedding.forward('statistical'), reference geoembed.py:37-41,80-84."""
     f = geo_statistical_features(source_pos, query_pos, edge_index)

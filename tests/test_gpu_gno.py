@@ -231,3 +231,29 @@ def test_geo_moments_compose_over_source_shards():
     z = ops.geo_from_moments(parts[0] + parts[1], normalize=True)
     zr = ogno.geo_statistical_features(torch.from_numpy(phys).double(), torch.from_numpy(lat).double(), ei, normalize=True)
     close(z, zr, rtol=2e-3, atol_rel=2e-4, what="z-scored features")
+
+
+@pytest.mark.parametrize("pooling", ["max", "mean"])
+def test_pointnet_embedding_golden(pooling):
+    """'pointnet' geometric embedding (reference geoembed.py:184-222): fused per-edge MLP + pool kernel against the
+    reference module's own output and parameter gradients (tests/golden/make_pointnet_golden.py) and the CPU oracle."""
+    from gaot_3d_b200.layers import GeometricEmbedding
+    gld = torch.load(os.path.join(GOLD, "pointnet_golden.pt"))[pooling]
+    ge = GeometricEmbedding(3, 16, method="pointnet", pooling=pooling).to(DEV)
+    ge.load_state_dict(gld["state"])                       # same parameter names as the reference
+    src, qry, ei = gld["source_pos"].to(DEV), gld["query_pos"].to(DEV), gld["edge_index"].to(DEV)
+    out = ge(src, qry, ei)
+    close(out, gld["out"], rtol=1e-5, atol_rel=2e-6, what="pointnet forward")
+    empty = (torch.bincount(gld["edge_index"][1], minlength=qry.shape[0]) == 0).to(DEV)
+    assert bool(empty.any()) and float(out.detach()[empty].abs().max()) == 0.0
+    out.backward(gld["d_out"].to(DEV))
+    for name, p in ge.named_parameters():
+        close(p.grad, gld["grads"][name], rtol=1e-4, atol_rel=2e-5, what=f"pointnet d {name}")
+    st = gld["state"]
+    ref = ogno.geo_pointnet_embedding(gld["source_pos"], gld["query_pos"], gld["edge_index"], st["pointnet_mlp.0.weight"],
+                                      st["pointnet_mlp.0.bias"], st["pointnet_mlp.2.weight"], st["pointnet_mlp.2.bias"],
+                                      st["fc.0.weight"], st["fc.0.bias"], pooling)
+    close(out, ref, rtol=1e-5, atol_rel=2e-6, what="pointnet vs oracle")
+    # no edges at all -> zeros, as the reference
+    z = ge(src, qry, torch.empty(2, 0, dtype=torch.long, device=DEV))
+    assert z.shape == out.shape and float(z.abs().max()) == 0.0

@@ -73,6 +73,16 @@ def test_restatements_match_reference_modules():
     ge = ref.geoembed.GeometricEmbedding(3, 8)
     a = ge._compute_statistical_features_pyg(y, x, ei)
     assert torch.allclose(a, ogno.geo_statistical_features(y, x, ei), rtol=1e-5, atol=1e-6)
+    # PointNet embedding, both poolings (queries without edges exist: 200 queries, some indices never drawn at E = 300)
+    ei2 = ei[:, :300]
+    for pooling in ("max", "mean"):
+        gp = ref.geoembed.GeometricEmbedding(3, 8, method="pointnet", pooling=pooling)
+        st = gp.state_dict()
+        a = gp(y, x, ei2)
+        b = ogno.geo_pointnet_embedding(y, x, ei2, st["pointnet_mlp.0.weight"], st["pointnet_mlp.0.bias"], st["pointnet_mlp.2.weight"],
+                                        st["pointnet_mlp.2.bias"], st["fc.0.weight"], st["fc.0.bias"], pooling)
+        assert torch.allclose(a, b, rtol=1e-6, atol=1e-7), pooling
+        assert float(b[torch.bincount(ei2[1], minlength=200) == 0].abs().max()) == 0.0
     # scatter_native mean with empty segments
     src, idx = torch.randn(50, 4), torch.randint(0, 9, (50,))
     assert torch.allclose(ref.scatter_native.scatter_native(src, idx, dim=0, dim_size=12, reduce="mean"), ogno.scatter_mean(src, idx, 12))
@@ -109,3 +119,14 @@ def test_config_schema_and_state_dict_keys_match_reference():
             assert list(sr) == list(so)
             assert all(sr[k].shape == so[k].shape for k in sr)
             mo.load_state_dict(sr, strict=True)
+
+
+def test_pointnet_golden_matches_oracle():
+    """The committed PointNet fixture (made by the reference module) against the CPU restatement: runs without /root/reference."""
+    g = torch.load(os.path.join(GOLD, "pointnet_golden.pt"))
+    for pooling, d in g.items():
+        st = d["state"]
+        out = ogno.geo_pointnet_embedding(d["source_pos"], d["query_pos"], d["edge_index"], st["pointnet_mlp.0.weight"],
+                                          st["pointnet_mlp.0.bias"], st["pointnet_mlp.2.weight"], st["pointnet_mlp.2.bias"],
+                                          st["fc.0.weight"], st["fc.0.bias"], pooling)
+        assert torch.allclose(out, d["out"], rtol=1e-6, atol=1e-7), pooling
