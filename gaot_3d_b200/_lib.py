@@ -43,6 +43,10 @@ _SIGS = {
                                  c_int, c_int, c_int, P, c_size_t, P, P]),
     "gaot_gno_backward": (c_int, [P, c_int64, P, c_int64, P, c_int32, P, P, P, c_int64, POINTER(MlpDesc), P,
                                   c_int, c_int, c_int, P, P, c_size_t, P, P, P]),
+    "gaot_gno_forward_weighted": (c_int, [P, c_int64, P, c_int64, P, c_int32, P, P, P, c_int64, POINTER(MlpDesc), P,
+                                          c_int, c_int, c_int, P, P, c_size_t, P, P]),
+    "gaot_gno_backward_weighted": (c_int, [P, c_int64, P, c_int64, P, c_int32, P, P, P, c_int64, POINTER(MlpDesc), P,
+                                           c_int, c_int, c_int, P, P, P, c_size_t, P, P, P, P]),
     "gaot_geo_stats": (c_int, [P, c_int64, P, c_int64, P, P, P, P]),
     "gaot_geo_moments": (c_int, [P, c_int64, P, c_int64, P, P, P, P]),
     "gaot_geo_from_moments": (c_int, [P, c_int64, P, P]),

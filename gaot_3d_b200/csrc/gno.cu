@@ -67,10 +67,21 @@ int gaot_gno_forward(const float* y_pos, int64_t n_src, const float* x_pos, int6
                      int32_t c_f, const int32_t* rowptr, const int32_t* csr_src, const int32_t* csr_qry,
                      int64_t E, const gaot_mlp_desc* mlp, const float* params, int transform, int reduce,
                      int precision, void* ws, size_t ws_bytes, float* out, void* stream) {
+    return gaot_gno_forward_weighted(y_pos, n_src, x_pos, nq, f_y, c_f, rowptr, csr_src, csr_qry, E, mlp, params, transform, reduce,
+                                     precision, nullptr, ws, ws_bytes, out, stream);
+}
+
+int gaot_gno_forward_weighted(const float* y_pos, int64_t n_src, const float* x_pos, int64_t nq, const float* f_y,
+                              int32_t c_f, const int32_t* rowptr, const int32_t* csr_src, const int32_t* csr_qry,
+                              int64_t E, const gaot_mlp_desc* mlp, const float* params, int transform, int reduce,
+                              int precision, const float* edge_w, void* ws, size_t ws_bytes, float* out, void* stream) {
     GnoArgs a;
     int rc = fill(a, y_pos, n_src, x_pos, nq, f_y, c_f, rowptr, csr_src, csr_qry, E, mlp, params, transform, reduce);
     if (rc) return rc;
-    if (precision == 0) return gno_forward_fp32(a, ws, ws_bytes, out, (cudaStream_t)stream);
+    GAOT_CHECK_ARG(edge_w == nullptr || reduce == 1, "gno: per-edge weights go with reduce = sum (integral_transform.py:165)");
+    a.edge_w = edge_w;
+    // the attentional variant runs on the FP32 kernels (the tensor-core kernels fold 1/count, not a per-edge weight)
+    if (precision == 0 || edge_w) return gno_forward_fp32(a, ws, ws_bytes, out, (cudaStream_t)stream);
     if (precision == 1) {
         if (use_gen2() && gno_forward_tc2_supported(a)) return gno_forward_tc2(a, ws, ws_bytes, out, (cudaStream_t)stream);
         if (gno_forward_bf16_supported(a)) return gno_forward_bf16(a, ws, ws_bytes, out, (cudaStream_t)stream);
@@ -85,10 +96,23 @@ int gaot_gno_backward(const float* y_pos, int64_t n_src, const float* x_pos, int
                       int64_t E, const gaot_mlp_desc* mlp, const float* params, int transform, int reduce,
                       int precision, const float* d_out, void* ws, size_t ws_bytes, float* d_params,
                       float* d_f_y, void* stream) {
+    return gaot_gno_backward_weighted(y_pos, n_src, x_pos, nq, f_y, c_f, rowptr, csr_src, csr_qry, E, mlp, params, transform, reduce,
+                                      precision, nullptr, d_out, ws, ws_bytes, d_params, d_f_y, nullptr, stream);
+}
+
+int gaot_gno_backward_weighted(const float* y_pos, int64_t n_src, const float* x_pos, int64_t nq, const float* f_y,
+                               int32_t c_f, const int32_t* rowptr, const int32_t* csr_src, const int32_t* csr_qry,
+                               int64_t E, const gaot_mlp_desc* mlp, const float* params, int transform, int reduce,
+                               int precision, const float* edge_w, const float* d_out, void* ws, size_t ws_bytes,
+                               float* d_params, float* d_f_y, float* d_edge_w, void* stream) {
     GnoArgs a;
     int rc = fill(a, y_pos, n_src, x_pos, nq, f_y, c_f, rowptr, csr_src, csr_qry, E, mlp, params, transform, reduce);
     if (rc) return rc;
     GAOT_CHECK_ARG(d_out != nullptr && d_params != nullptr, "gno_backward: null gradient buffers");
+    GAOT_CHECK_ARG(edge_w != nullptr || d_edge_w == nullptr, "gno_backward: d_edge_w without edge_w");
+    GAOT_CHECK_ARG(edge_w == nullptr || reduce == 1, "gno: per-edge weights go with reduce = sum");
+    a.edge_w = edge_w; a.d_edge_w = d_edge_w;
+    if (edge_w) return gno_backward_fp32(a, d_out, ws, ws_bytes, d_params, d_f_y, (cudaStream_t)stream);
     // precision 1: tensor-core backward when the MLP fits its envelope, otherwise the FP32 recompute
     if (precision == 1 && use_gen2() && gno_backward_tc2_supported(a))
         return gno_backward_tc2(a, d_out, ws, ws_bytes, d_params, d_f_y, (cudaStream_t)stream);

@@ -207,7 +207,18 @@ gno_bwd_fp32_kernel(const GnoArgs a, const BwdSmemLayout L, const float* __restr
                 if (active && e < ne) {
                     const int q = s_qry[e];
                     g = *reinterpret_cast<const float4*>(d_out + (size_t)q * Cout + jF);
-                    if (a.reduce == 0) {
+                    if (a.edge_w) {
+                        if (a.d_edge_w) {                  // d loss / d w_e = <d_out[q], k_e (* f_e)>: 4 of the Cout terms here
+                            float4 kf = make_float4(kacc[m][0], kacc[m][1], kacc[m][2], kacc[m][3]);
+                            if (use_f_mul) {
+                                const float4 f = *reinterpret_cast<const float4*>(fsm + e * a.c_f + jF);
+                                kf.x *= f.x; kf.y *= f.y; kf.z *= f.z; kf.w *= f.w;
+                            }
+                            atomicAdd(a.d_edge_w + e0 + e, g.x * kf.x + g.y * kf.y + g.z * kf.z + g.w * kf.w);
+                        }
+                        const float w = a.edge_w[e0 + e];
+                        g.x *= w; g.y *= w; g.z *= w; g.w *= w;
+                    } else if (a.reduce == 0) {
                         const float inv = 1.0f / (float)(a.rowptr[q + 1] - a.rowptr[q]);
                         g.x *= inv; g.y *= inv; g.z *= inv; g.w *= inv;
                     }
@@ -371,6 +382,7 @@ int gno_backward_fp32(const GnoArgs& a_in, const float* d_out, void* ws, size_t 
     GnoArgs a = a_in;
     a.ntiles = (a.E + BTE - 1) / BTE;
     if (d_f) GAOT_CUDA(cudaMemsetAsync(d_f, 0, (size_t)a.n_src * a.c_f * sizeof(float), st));
+    if (a.d_edge_w && a.E > 0) GAOT_CUDA(cudaMemsetAsync(a.d_edge_w, 0, (size_t)a.E * sizeof(float), st));
     if (a.E == 0) {
         GAOT_CUDA(cudaMemsetAsync(d_params, 0, (size_t)a.n_params * sizeof(float), st));
         return GAOT_OK;

@@ -12,6 +12,8 @@ struct GnoArgs {
     const float* y_pos; const float* x_pos; const float* f_y;
     const int32_t* rowptr; const int32_t* csr_src; const int32_t* csr_qry;
     const float* params;
+    const float* edge_w;                // optional per-edge weight in CSR order (attentional integral: replaces 1/count, reduce = sum)
+    float* d_edge_w;                    // optional: d loss / d edge_w (backward; zero-initialised by the launcher)
     int32_t E, nq, n_src, c_f;
     int32_t n_layers;
     int32_t dims[GNO_MAX_LAYERS + 1];

@@ -191,6 +191,10 @@ gno_fwd_fp32_kernel(const GnoArgs a, const FwdSmemLayout L, float* __restrict__ 
                             const float4 f = *reinterpret_cast<const float4*>(fsm + e * a.c_f + j0);
                             v.x *= f.x; v.y *= f.y; v.z *= f.z; v.w *= f.w;
                         }
+                        if (a.edge_w && e < ne) {          // attention weight of the edge (integral_transform.py:161-162)
+                            const float w = a.edge_w[e0 + e];
+                            v.x *= w; v.y *= w; v.z *= w; v.w *= w;
+                        }
                         *reinterpret_cast<float4*>(outb + e * CP + j0) = v;
                     }
                 }

@@ -29,9 +29,15 @@ class IntegralTransform(nn.Module):
         self.channel_mlp = channel_mlp
         if channel_mlp_non_linearity is not F.gelu:
             raise NotImplementedError("the fused GNO kernel implements the reference's exact-erf GELU only")
-        if self.use_attn:
-            # segment-softmax attention weights are a later row
-            raise NotImplementedError("use_attn (segment-softmax GNO weights) is not built yet; the reference default is None")
+        if self.use_attn:                                   # reference :53-66
+            if coord_dim is None:
+                raise ValueError("coord_dim must be specified when use_attn is True")
+            if attention_type == "dot_product":
+                self.query_proj = nn.Linear(coord_dim, 64)
+                self.key_proj = nn.Linear(coord_dim, 64)
+                self.scaling_factor = 1.0 / (64 ** 0.5)
+            elif attention_type != "cosine":
+                raise ValueError(f"Invalid attention_type: {attention_type}. Must be 'cosine' or 'dot_product'.")
         if transform_type not in ("linear", "nonlinear", "nonlinear_kernelonly"):
             raise ValueError(f"unknown transform_type {transform_type}")
 
@@ -47,5 +53,22 @@ class IntegralTransform(nn.Module):
         if edge_index.shape[1] == 0:                       # reference :107-112
             return torch.zeros(nq, fcs[-1].out_features, device=device, dtype=fcs[-1].weight.dtype)
         csr = ops.csr_of(edge_index, y_pos.shape[0], nq)
+        edge_w = self._attention_weights(y_pos, x_pos, csr) if self.use_attn else None
         return ops.gno(y_pos, x_pos, f_y, csr, [fc.weight for fc in fcs], [fc.bias for fc in fcs],
-                       transform_type=self.transform_type, reduce=reduce)
+                       transform_type=self.transform_type, reduce=reduce, edge_w=edge_w)
+
+    def _attention_weights(self, y_pos, x_pos, csr):
+        """Per-edge weights of the attentional integral (reference :128-141 scores, :68-78 segment softmax), in the
+        CSR edge order the fused kernel walks.  Scores are a few device-side torch ops on [E, coord_dim]; the integral
+        itself (gather, kernel MLP, weighting, segmented sum) stays one fused kernel."""
+        qry, src = csr.qry.long(), csr.src.long()
+        qc, kc = x_pos[qry][:, :self.coord_dim], y_pos[src][:, :self.coord_dim]
+        if self.attention_type == "dot_product":
+            scores = (self.query_proj(qc) * self.key_proj(kc)).sum(-1) * self.scaling_factor
+        else:
+            scores = (F.normalize(qc, p=2, dim=-1) * F.normalize(kc, p=2, dim=-1)).sum(-1)
+        nq = x_pos.shape[0]
+        smax = torch.zeros(nq, dtype=scores.dtype, device=scores.device).scatter_reduce(0, qry, scores.detach(), reduce="amax", include_self=False)
+        ex = torch.exp(scores - smax[qry])
+        den = torch.zeros(nq, dtype=ex.dtype, device=ex.device).index_add(0, qry, ex).clamp(min=torch.finfo(ex.dtype).tiny)
+        return ex / den[qry]

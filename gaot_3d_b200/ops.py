@@ -281,7 +281,7 @@ def _flat_params(weights, biases) -> torch.Tensor:
 
 class _GnoFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, y_pos, x_pos, f_y, csr: Csr, dims, transform, reduce, precision, *wb):
+    def forward(ctx, y_pos, x_pos, f_y, csr: Csr, dims, transform, reduce, precision, edge_w, *wb):
         nl = len(dims) - 1
         weights, biases = wb[:nl], wb[nl:]
         params = _flat_params(weights, biases)
@@ -294,11 +294,13 @@ class _GnoFn(torch.autograd.Function):
         out = torch.empty(nq, dims[-1], dtype=torch.float32, device=dev)
         wsb = lib.gaot_gno_workspace_bytes(E, nq, ctypes.byref(desc))
         ws = _ws(wsb, dev)
+        ew = None if edge_w is None else edge_w.detach().to(torch.float32).contiguous()
         with torch.cuda.device(dev), _timed("gno_fwd", dev):
-            check(lib.gaot_gno_forward(_p(y_pos), n_src, _p(x_pos), nq, _p(fy), c_f, _p(csr.rowptr), _p(csr.src),
-                                       _p(csr.qry), E, ctypes.byref(desc), _p(params), transform, reduce, precision,
-                                       _p(ws), wsb, _p(out), _stream(dev)), "gno_forward")
-        ctx.save_for_backward(y_pos, x_pos, fy, params)
+            check(lib.gaot_gno_forward_weighted(_p(y_pos), n_src, _p(x_pos), nq, _p(fy), c_f, _p(csr.rowptr), _p(csr.src),
+                                                _p(csr.qry), E, ctypes.byref(desc), _p(params), transform, reduce, precision,
+                                                _p(ew), _p(ws), wsb, _p(out), _stream(dev)), "gno_forward")
+        ctx.save_for_backward(y_pos, x_pos, fy, params, ew)
+        ctx.need_ew = edge_w is not None and edge_w.requires_grad
         ctx.csr, ctx.dims, ctx.transform, ctx.reduce, ctx.precision = csr, dims, transform, reduce, precision
         ctx.need_f = f_y is not None and f_y.requires_grad
         ctx.shapes = [(tuple(w.shape), tuple(b.shape)) for w, b in zip(weights, biases)]
@@ -306,7 +308,7 @@ class _GnoFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_out):
-        y_pos, x_pos, fy, params = ctx.saved_tensors
+        y_pos, x_pos, fy, params, ew = ctx.saved_tensors
         csr, dims = ctx.csr, ctx.dims
         dev = x_pos.device
         lib = _lib_()
@@ -317,22 +319,27 @@ class _GnoFn(torch.autograd.Function):
         d_f = torch.empty_like(fy) if ctx.need_f else None
         wsb = lib.gaot_gno_workspace_bytes(csr.E, csr.nq, ctypes.byref(desc))
         ws = _ws(wsb, dev)
+        d_ew = torch.empty_like(ew) if (ew is not None and ctx.need_ew) else None
         with torch.cuda.device(dev), _timed("gno_bwd", dev):
-            check(lib.gaot_gno_backward(_p(y_pos), csr.n_src, _p(x_pos), csr.nq, _p(fy), c_f, _p(csr.rowptr),
-                                        _p(csr.src), _p(csr.qry), csr.E, ctypes.byref(desc), _p(params),
-                                        ctx.transform, ctx.reduce, ctx.precision, _p(d_out), _p(ws), wsb,
-                                        _p(d_params), _p(d_f), _stream(dev)), "gno_backward")
+            check(lib.gaot_gno_backward_weighted(_p(y_pos), csr.n_src, _p(x_pos), csr.nq, _p(fy), c_f, _p(csr.rowptr),
+                                                 _p(csr.src), _p(csr.qry), csr.E, ctypes.byref(desc), _p(params),
+                                                 ctx.transform, ctx.reduce, ctx.precision, _p(ew), _p(d_out), _p(ws), wsb,
+                                                 _p(d_params), _p(d_f), _p(d_ew), _stream(dev)), "gno_backward")
         gw, gb, off = [], [], 0
         for (ws_, bs_) in ctx.shapes:
             nw = ws_[0] * ws_[1]
             gw.append(d_params[off: off + nw].view(ws_)); off += nw
             gb.append(d_params[off: off + bs_[0]].view(bs_)); off += bs_[0]
-        return (None, None, d_f, None, None, None, None, None, *gw, *gb)
+        return (None, None, d_f, None, None, None, None, None, d_ew, *gw, *gb)
 
 
 def gno(y_pos, x_pos, f_y, csr: Csr, weights, biases, transform_type: str = "linear",
-        reduce: str = "mean", precision: Optional[str] = None) -> torch.Tensor:
-    """Fused gather -> kernel MLP -> (* f_y) -> segmented mean (reference integral_transform.py:114-171)."""
+        reduce: str = "mean", precision: Optional[str] = None, edge_w: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fused gather -> kernel MLP -> (* f_y) -> segmented mean (reference integral_transform.py:114-171).
+    `edge_w` [E] (CSR order, see Csr.src / Csr.qry): per-edge attention weights multiplied in before a SUM reduction
+    (use_attn, :161-165); differentiable."""
+    if edge_w is not None:
+        reduce = "sum"
     _need_cuda(y_pos, x_pos, f_y)
     if f_y is None:
         t = 3
@@ -343,7 +350,7 @@ def gno(y_pos, x_pos, f_y, csr: Csr, weights, biases, transform_type: str = "lin
     dims = [int(weights[0].shape[1])] + [int(w.shape[0]) for w in weights]
     prec = _PRECISION["gno"] if precision is None else (0 if precision == "fp32" else 1)
     return _GnoFn.apply(_pos3(y_pos), _pos3(x_pos), f_y, csr, tuple(dims), t, 0 if reduce == "mean" else 1, prec,
-                        *weights, *biases)
+                        edge_w, *weights, *biases)
 
 
 # ----------------------------------------------------------------------------- geometric embedding

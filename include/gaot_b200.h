@@ -136,6 +136,20 @@ int gaot_gno_backward(const float* y_pos, int64_t n_src, const float* x_pos, int
                       const float* d_out, void* ws, size_t ws_bytes,
                       float* d_params, float* d_f_y, void* stream);
 
+/* Attentional integral transform (reference integral_transform.py:128-141,:161-165, use_attn): the same fused kernels with
+ * a per-edge weight (CSR order) multiplied into each edge's value before a SUM reduction (reduce must be 1); the weights
+ * are the segment-softmax of the cosine / projected-dot scores, computed by the host.  The backward optionally returns
+ * d loss / d edge_w [E] (needed for the learnable 'dot_product' projections).  These run on the FP32 kernels. */
+int gaot_gno_forward_weighted(const float* y_pos, int64_t n_src, const float* x_pos, int64_t nq, const float* f_y,
+                              int32_t c_f, const int32_t* rowptr, const int32_t* csr_src, const int32_t* csr_qry,
+                              int64_t E, const gaot_mlp_desc* mlp, const float* params, int transform, int reduce,
+                              int precision, const float* edge_w, void* ws, size_t ws_bytes, float* out, void* stream);
+int gaot_gno_backward_weighted(const float* y_pos, int64_t n_src, const float* x_pos, int64_t nq, const float* f_y,
+                               int32_t c_f, const int32_t* rowptr, const int32_t* csr_src, const int32_t* csr_qry,
+                               int64_t E, const gaot_mlp_desc* mlp, const float* params, int transform, int reduce,
+                               int precision, const float* edge_w, const float* d_out, void* ws, size_t ws_bytes,
+                               float* d_params, float* d_f_y, float* d_edge_w, void* stream);
+
 /* ------------------------------------------------------------------ geometric embedding statistics
  * Replaces the 5 scatters + batched eigvalsh of reference src/model/layers/geoembed.py:99-175:
  * per query [N_i, mean|y-x|, var|y-x|, centroid - x (3), eig(cov + 1e-6 I) descending (3)],

@@ -35,10 +35,20 @@ def mlp_forward(x, weights, biases):
     return x
 
 
-def integral_transform(y_pos, x_pos, edge_index, f_y, weights, biases, transform_type="linear"):
-    """IntegralTransform.forward, reference integral_transform.py:80-175 (use_attn=None path).
+def segment_softmax(scores, index, dim_size):
+    """IntegralTransform._segment_softmax_pyg, reference integral_transform.py:68-78."""
+    smax = torch.zeros(dim_size, dtype=scores.dtype).scatter_reduce(0, index, scores, reduce="amax", include_self=False)
+    ex = torch.exp(scores - smax[index])
+    den = torch.clamp(scatter_sum(ex, index, dim_size), min=torch.finfo(ex.dtype).tiny)
+    return ex / den[index]
+
+
+def integral_transform(y_pos, x_pos, edge_index, f_y, weights, biases, transform_type="linear", attn=None):
+    """IntegralTransform.forward, reference integral_transform.py:80-175.
 
     out[q] = mean_{e: qry(e)=q} MLP(cat[y_pos[src], x_pos[q] (, f_y[src])]) (* f_y[src])
+    attn = dict(type='cosine' | 'dot_product', coord_dim=D[, wq, bq, wk, bk]) selects the attentional variant
+    (use_attn, :128-141): the per-edge values are weighted by the segment softmax of the scores and SUMMED (:161-165).
     """
     nq = x_pos.shape[0]
     if edge_index.shape[1] == 0:                                   # :107-112
@@ -52,6 +62,14 @@ def integral_transform(y_pos, x_pos, edge_index, f_y, weights, biases, transform
     k = mlp_forward(agg, weights, biases)                          # :154
     if inf is not None and transform_type != "nonlinear_kernelonly":
         k = k * inf                                                # :156-157
+    if attn is not None:
+        d = attn["coord_dim"]
+        qc, kc = slf[:, :d], rep[:, :d]                            # :130-131
+        if attn["type"] == "dot_product":                          # :132-135
+            sc = (F.linear(qc, attn["wq"], attn["bq"]) * F.linear(kc, attn["wk"], attn["bk"])).sum(-1) / (attn["wq"].shape[0] ** 0.5)
+        else:                                                      # :136-139
+            sc = (F.normalize(qc, p=2, dim=-1) * F.normalize(kc, p=2, dim=-1)).sum(-1)
+        return scatter_sum(k * segment_softmax(sc, qry, nq).unsqueeze(-1), qry, nq)    # :141, :161-171 (reduce='sum')
     return scatter_mean(k, qry, nq)                                # :163-171 (reduce='mean')
 
 

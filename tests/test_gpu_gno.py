@@ -257,3 +257,38 @@ def test_pointnet_embedding_golden(pooling):
     # no edges at all -> zeros, as the reference
     z = ge(src, qry, torch.empty(2, 0, dtype=torch.long, device=DEV))
     assert z.shape == out.shape and float(z.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("attention_type", ["cosine", "dot_product"])
+def test_gno_attentional_transform(attention_type):
+    """use_attn (reference integral_transform.py:128-141,:161-165): segment-softmax edge weights, SUM reduction; the
+    fused kernel takes the weights per CSR edge.  Against the fp64 oracle: output, d f_y, kernel-MLP gradients and (for
+    'dot_product') the gradients of the learnable score projections."""
+    from gaot_3d_b200.layers import IntegralTransform
+    torch.manual_seed(3)
+    phys, lat = synth.surface_cloud(6000, seed=6), synth.latent_grid((8, 8, 8))
+    ei = torch.from_numpy(og.radius_np(phys, lat, 0.25, workers=-1)[::-1].copy())            # [phys, latent]
+    ypos, xpos = torch.from_numpy(phys), torch.from_numpy(lat)
+    it = IntegralTransform(channel_mlp_layers=[6, 64, 64, 32], use_attn=True, coord_dim=3, attention_type=attention_type).to(DEV)
+    f = torch.randn(ypos.shape[0], 32)
+    fd = f.to(DEV).requires_grad_(True)
+    out = it(ypos.to(DEV), xpos.to(DEV), ei.to(DEV), fd)
+    params = {n: p.detach().cpu().double().requires_grad_(True) for n, p in it.named_parameters()}
+    attn = dict(type=attention_type, coord_dim=3)
+    if attention_type == "dot_product":
+        attn.update(wq=params["query_proj.weight"], bq=params["query_proj.bias"], wk=params["key_proj.weight"], bk=params["key_proj.bias"])
+    fr = f.double().requires_grad_(True)
+    ws = [params[f"channel_mlp.fcs.{i}.weight"] for i in range(3)]
+    bs = [params[f"channel_mlp.fcs.{i}.bias"] for i in range(3)]
+    ref = ogno.integral_transform(ypos.double(), xpos.double(), ei, fr, ws, bs, attn=attn)
+    close(out, ref, rtol=1e-5, atol_rel=4e-6, what="attentional forward")
+    g = torch.randn_like(ref)
+    ref.backward(g)
+    out.backward(g.float().to(DEV))
+    close(fd.grad, fr.grad, rtol=2e-5, atol_rel=1e-5, what="d_f")
+    for n, p in it.named_parameters():
+        if n == "key_proj.bias":
+            # a bias on the keys shifts every score of a segment by the same amount: softmax-invariant, gradient == 0
+            assert float(params[n].grad.abs().max()) < 1e-12 and float(p.grad.abs().max()) < 1e-5
+            continue
+        close(p.grad, params[n].grad, rtol=1e-4, atol_rel=5e-5, what=f"d {n}")

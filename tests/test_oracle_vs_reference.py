@@ -70,6 +70,16 @@ def test_restatements_match_reference_modules():
         a = it(y, x, ei, f)
         b = ogno.integral_transform(y, x, ei, f, [l.weight for l in it.channel_mlp.fcs], [l.bias for l in it.channel_mlp.fcs], tt)
         assert torch.allclose(a, b, rtol=1e-6, atol=1e-7), tt
+    # attentional integral transform (use_attn), both score types
+    for at in ("cosine", "dot_product"):
+        it = ref.integral_transform.IntegralTransform(channel_mlp_layers=[6, 32, 16], use_attn=True, coord_dim=3, attention_type=at)
+        f = torch.randn(800, 16)
+        a = it(y, x, ei, f)
+        attn = dict(type=at, coord_dim=3)
+        if at == "dot_product":
+            attn.update(wq=it.query_proj.weight, bq=it.query_proj.bias, wk=it.key_proj.weight, bk=it.key_proj.bias)
+        b = ogno.integral_transform(y, x, ei, f, [l.weight for l in it.channel_mlp.fcs], [l.bias for l in it.channel_mlp.fcs], attn=attn)
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), at
     ge = ref.geoembed.GeometricEmbedding(3, 8)
     a = ge._compute_statistical_features_pyg(y, x, ei)
     assert torch.allclose(a, ogno.geo_statistical_features(y, x, ei), rtol=1e-5, atol=1e-6)
