@@ -23,7 +23,7 @@ Restates, in numpy (exact fp32 arithmetic, int64 indices):
   flips, bidirectional = coalesce(cat(knn, radius)), reverse = flip of the
   *bidirectional* encoder graph (magno.py:263-273).
 
-PARITY PINNING: the reference ships no tests / golden vectors for this path
+PARITY UNPINNED against a real torch_cluster install -- the reference ships no tests / golden vectors for this path
  and torch_cluster is absent from this image, so this
 restatement is pinned (a) against an independent brute-force O(N*M) evaluation
 of the same definition (tests/test_oracle_graph.py) and (b) against the
