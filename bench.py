@@ -238,7 +238,7 @@ def main():
         model_step = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank])
     else:
         model_step = model
-    opt = torch.optim.AdamW(model.parameters(), lr=3e-4, weight_decay=1e-5)
+    opt = torch.optim.AdamW(model.parameters(), lr=3e-4, weight_decay=1e-5, fused=True)
     lat = torch.from_numpy(synth.latent_grid(wl["latent"], wl["box"])).to(dev)
     host = []
     n_total = wl["n_points"]

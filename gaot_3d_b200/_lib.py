@@ -71,6 +71,7 @@ _SIGS = {
     "gaot_linear_backward_weight": (c_int, [P, c_int, c_int64, P, c_int, c_int64, c_int64, c_int64, c_int64,
                                             P, c_int64, c_int, P, c_size_t, P]),
     "gaot_cast_bf16": (c_int, [P, P, c_int64, P]),
+    "gaot_cast_bf16_batch": (c_int, [P, P, P, c_int32, P]),
     "gaot_rmsnorm_forward": (c_int, [P, P, c_int64, c_int32, c_float, P, P, P, P]),
     "gaot_rmsnorm_backward_workspace_bytes": (c_size_t, [c_int32]),
     "gaot_rmsnorm_backward": (c_int, [P, P, P, P, P, c_int64, c_int32, P, P, P, c_size_t, P]),

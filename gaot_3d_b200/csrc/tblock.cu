@@ -27,6 +27,22 @@ cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t 
     reinterpret_cast<uint4*>(dst)[i] = o;
 }
 
+// several casts in one launch (the weights of one transformer block): blockIdx.y selects the segment
+struct CastBatch { const float* src[8]; bf16* dst[8]; int64_t n8[8]; };
+__global__ void __launch_bounds__(256)
+cast_bf16_batch_kernel(const CastBatch cb) {
+    const int s = blockIdx.y;
+    const int64_t n8 = cb.n8[s];
+    const float4* src = reinterpret_cast<const float4*>(cb.src[s]);
+    uint4* dst = reinterpret_cast<uint4*>(cb.dst[s]);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 a = __ldg(src + 2 * i), b = __ldg(src + 2 * i + 1);
+        uint4 o;
+        o.x = tc::pack_bf16(a.x, a.y); o.y = tc::pack_bf16(a.z, a.w); o.z = tc::pack_bf16(b.x, b.y); o.w = tc::pack_bf16(b.z, b.w);
+        dst[i] = o;
+    }
+}
+
 // ---- RMSNorm: y = x * rsqrt(mean(x^2) + eps) * w   (fp32 statistics, reference attn.py:175-178) ----
 // NV = H / 128 float4 per lane (H = 128 * NV)
 template <int NV>
@@ -217,6 +233,23 @@ int gaot_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
     GAOT_CHECK_ARG(n % 8 == 0, "cast_bf16: n must be a multiple of 8");
     if (n == 0) return GAOT_OK;
     cast_bf16_kernel<<<nblk(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n / 8);
+    GAOT_LAUNCH_CHECK();
+    return GAOT_OK;
+}
+
+int gaot_cast_bf16_batch(const float* const* src, void* const* dst, const int64_t* n, int32_t count, void* stream) {
+    GAOT_CHECK_ARG(count >= 0 && count <= 8, "cast_bf16_batch: at most 8 segments per call");
+    if (count == 0) return GAOT_OK;
+    CastBatch cb;
+    int64_t nmax = 0;
+    for (int i = 0; i < count; ++i) {
+        GAOT_CHECK_ARG(n[i] % 8 == 0, "cast_bf16_batch: segment lengths must be multiples of 8");
+        cb.src[i] = src[i]; cb.dst[i] = (bf16*)dst[i]; cb.n8[i] = n[i] / 8;
+        nmax = cb.n8[i] > nmax ? cb.n8[i] : nmax;
+    }
+    if (nmax == 0) return GAOT_OK;
+    const unsigned gx = (unsigned)std::min<int64_t>((nmax + 255) / 256, 64);
+    cast_bf16_batch_kernel<<<dim3(gx, (unsigned)count), 256, 0, (cudaStream_t)stream>>>(cb);
     GAOT_LAUNCH_CHECK();
     return GAOT_OK;
 }

@@ -66,6 +66,25 @@ def _cast_into(src: torch.Tensor, dst: torch.Tensor) -> None:
     check(lib.gaot_cast_bf16(_p(s), _p(dst), s.numel(), _stream(s.device)), "cast_bf16")
 
 
+def _cast_many(pairs) -> None:
+    """[(fp32 parameter, bf16 destination view)] -> one launch per <= 8 casts (the weights of a block are cast once per call)."""
+    lib = _lib_()
+    srcs = []
+    for s, d in pairs:
+        s = s.detach()
+        if s.dtype != torch.float32 or not s.is_contiguous():
+            s = s.to(torch.float32).contiguous()
+        assert d.is_contiguous() and d.numel() == s.numel()
+        srcs.append((s, d))
+    for i in range(0, len(srcs), 8):
+        chunk = srcs[i:i + 8]
+        n = len(chunk)
+        a_src = (ctypes.c_void_p * n)(*[s.data_ptr() for s, _ in chunk])
+        a_dst = (ctypes.c_void_p * n)(*[d.data_ptr() for _, d in chunk])
+        a_n = (ctypes.c_int64 * n)(*[s.numel() for s, _ in chunk])
+        check(lib.gaot_cast_bf16_batch(a_src, a_dst, a_n, n, _stream(chunk[0][0].device)), "cast_bf16_batch")
+
+
 def _cast(src: torch.Tensor) -> torch.Tensor:
     dst = torch.empty(src.shape, dtype=BF16, device=src.device)
     _cast_into(src, dst)
@@ -126,18 +145,23 @@ class _BlockFn(torch.autograd.Function):
         f32 = lambda t: t.detach().to(torch.float32).contiguous()
         with torch.cuda.device(dev):
             x2d = f32(x).view(M, Hd)
+            # every weight of the block -> bf16 operands in ONE launch (q/k/v and w1/w3 land in concatenated operands)
+            nq, nkv, F = H * d, Hkv * d, w1.shape[0]
+            wqkv = torch.empty(nq + 2 * nkv, Hd, dtype=BF16, device=dev)
+            w13 = torch.empty(2 * F, Hd, dtype=BF16, device=dev)
+            wob = torch.empty(wo.shape, dtype=BF16, device=dev)
+            w2b = torch.empty(w2.shape, dtype=BF16, device=dev)
+            wsk = torch.empty(skip_w.shape, dtype=BF16, device=dev) if skip is not None else None
+            _cast_many([(wq, wqkv[:nq]), (wk, wqkv[nq:nq + nkv]), (wv, wqkv[nq + nkv:]), (wo, wob), (w1, w13[:F]), (w3, w13[F:]),
+                        (w2, w2b)] + ([(skip_w, wsk)] if skip is not None else []))
             if skip is not None:
                 s2d = f32(skip).view(M, -1)
-                wsk = _cast(skip_w)
                 x_in = _linear_fwd_raw(x2d, s2d, wsk, f32(skip_b) if skip_b is not None else None, None)
             else:
-                s2d = wsk = None
+                s2d = None
                 x_in = x2d
             n1, n2 = f32(n1_w), f32(n2_w)
             h1, _, rstd1 = _rmsnorm_fwd(x_in, n1, eps, False)
-            nq, nkv = H * d, Hkv * d
-            wqkv = torch.empty(nq + 2 * nkv, Hd, dtype=BF16, device=dev)
-            _cast_into(wq, wqkv[:nq]); _cast_into(wk, wqkv[nq:nq + nkv]); _cast_into(wv, wqkv[nq + nkv:])
             qkv = _linear_fwd_raw(h1, None, wqkv, None, None, BF16)
             Ha, Hkva = H, Hkv                                                   # heads this rank runs through the attention core
             if hp is not None:
@@ -156,16 +180,11 @@ class _BlockFn(torch.autograd.Function):
             del qkv
             if hp is not None:
                 o = torch.cat(_gather_cols(o, hp[1], hp[2]), dim=1)            # [M, H*d]: every rank's heads, in head order
-            wob = _cast(wo)
             h = _linear_fwd_raw(o, None, wob, None, x_in)                       # x + attn(norm(x))
             h2b, h2, rstd2 = _rmsnorm_fwd(h, n2, eps, True)
-            F = w1.shape[0]
-            w13 = torch.empty(2 * F, Hd, dtype=BF16, device=dev)
-            _cast_into(w1, w13[:F]); _cast_into(w3, w13[F:])
             gu = _linear_fwd_raw(h2b, None, w13, None, None, BF16)
             a = torch.empty(M, F, dtype=BF16, device=dev)
             check(lib.gaot_swiglu_forward(_p(gu), M, F, _p(a), _stream(dev)), "swiglu_forward")
-            w2b = _cast(w2)
             out = _linear_fwd_raw(a, None, w2b, None, h2)                       # h2 + ffn(h2)
         ctx.save_for_backward(x2d, s2d, x_in, rstd1, h1, packed, o, o32, lse, h, rstd2, h2b, gu, a,
                               wsk, wqkv, wob, w13, w2b, n1, n2, fr)

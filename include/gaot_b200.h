@@ -252,6 +252,8 @@ int gaot_linear_backward_weight(const void* dy, int dy_dtype, int64_t lddy, cons
  *   colsum: bias gradient of skip_proj (:223).   cast_bf16: fp32 weights -> bf16 tensor-core operands.
  */
 int gaot_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+/* up to 8 independent casts in one launch (all weights of one transformer block); host arrays of device pointers */
+int gaot_cast_bf16_batch(const float* const* src, void* const* dst_bf16, const int64_t* n, int32_t count, void* stream);
 int gaot_rmsnorm_forward(const float* x, const float* w, int64_t M, int32_t H, float eps,
                          void* y_bf16 /* may be NULL */, float* y_f32 /* may be NULL */, float* rstd /* [M] */, void* stream);
 size_t gaot_rmsnorm_backward_workspace_bytes(int32_t H);
