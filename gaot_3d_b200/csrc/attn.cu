@@ -1065,7 +1065,9 @@ constexpr int SMEM = OFF_STG + 4 * 4096;            // 212992 B
 constexpr uint32_t TM_DV = 256, TM_DK = 288, TM_DQ = 320;
 }
 
-template <int NCW, bool DROP>
+// PADK: the sequence has padding keys (S % 128 != 0) -> per-element validity select; EMU: of every 32 exponentials this many
+// run as the FMA-pipe polynomial (ex2_poly)
+template <int NCW, bool DROP, bool PADK = true, int EMU = 0>
 __global__ void __launch_bounds__((NCW + 6) * 32, 1)
 attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const bf16* __restrict__ Vb,
                  const bf16* __restrict__ dOb, const float* __restrict__ Dvec,
@@ -1251,7 +1253,7 @@ attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const
         // ------------------------------------------------------------------ compute warps
         const int quarter = warp & 3, cg = warp >> 2;
         const int row = quarter * 32 + lane, key = k0 + row;
-        const bool valid_k = key < S;
+        const bool valid_k = PADK ? key < S : true;
         const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
         const int c0 = cg * CPT;
         const uint32_t kterm = (uint32_t)key * 0x85EBCA6Bu;
@@ -1277,7 +1279,9 @@ attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const int cc = c8 * 8 + c;
-                    p[c] = valid_k ? ex2_approx(__uint_as_float(r0[cc])) : 0.f;      // padding keys: P = dS = 0
+                    const bool emu = ((cc + 1) * EMU) / 32 > (cc * EMU) / 32;
+                    const float e = emu ? ex2_poly(__uint_as_float(r0[cc])) : ex2_approx(__uint_as_float(r0[cc]));
+                    p[c] = valid_k ? e : 0.f;                              // padding keys: P = dS = 0
                     if (DROP) {
                         const int qi = hq * 64 + c0 + cc;
                         const float mk = (lowbias32(rk_s[i % NLB][qi] ^ kterm) >= dc.thresh) ? dc.inv_keep : 0.f;
@@ -1477,7 +1481,19 @@ static int attn_launch_bwd(const AttnWs& w, const float* lse, int64_t B, int64_t
     do { GAOT_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<NCW, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bw2::SMEM)); \
          attn_bwd2_kernel<NCW, DR><<<grid, (NCW + 6) * 32, bw2::SMEM, st>>>(w.Qb, w.Kb, w.Vb, w.dOb, w.Dvec, w.dQacc, w.dKh, w.dVh, \
                                                                            (int)S, H, Hkv, scale, scale_dk, dc); } while (0)
-        if (drop) GAOT_BWD2_LAUNCH(16, true); else GAOT_BWD2_LAUNCH(16, false);
+        // GAOT_ATTN_BWD_EMU = 0 / 4 / 8 (of every 32 exponentials on the FMA pipe); sequences without padding keys skip the
+        // per-element validity select
+        static const int bemu = getenv("GAOT_ATTN_BWD_EMU") ? atoi(getenv("GAOT_ATTN_BWD_EMU")) : 0;
+#define GAOT_BWD2_LAUNCH4(PK, EM)                                                                                      \
+    do { GAOT_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<16, false, PK, EM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bw2::SMEM)); \
+         attn_bwd2_kernel<16, false, PK, EM><<<grid, (16 + 6) * 32, bw2::SMEM, st>>>(w.Qb, w.Kb, w.Vb, w.dOb, w.Dvec, w.dQacc, w.dKh, w.dVh, \
+                                                                                    (int)S, H, Hkv, scale, scale_dk, dc); } while (0)
+        if (drop) GAOT_BWD2_LAUNCH(16, true);
+        else if (S % 128 != 0) GAOT_BWD2_LAUNCH(16, false);
+        else if (bemu >= 8) GAOT_BWD2_LAUNCH4(false, 8);
+        else if (bemu >= 4) GAOT_BWD2_LAUNCH4(false, 4);
+        else GAOT_BWD2_LAUNCH4(false, 0);
+#undef GAOT_BWD2_LAUNCH4
 #undef GAOT_BWD2_LAUNCH
         GAOT_LAUNCH_CHECK();
         return GAOT_OK;
