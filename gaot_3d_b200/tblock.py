@@ -50,6 +50,21 @@ def _head_shard(num_heads: int, num_kv_heads: int):
     return dist.get_rank(grp), R, grp
 
 
+def head_slices(qkv: torch.Tensor, r: int, R: int, H: int, Hkv: int, d: int) -> torch.Tensor:
+    """[M, (H + 2 Hkv) d] = [q | k | v] of all heads -> the contiguous [q_l | k_l | v_l] block of rank r's heads
+    (heads [r H/R, (r+1) H/R) and their kv heads [r Hkv/R, (r+1) Hkv/R): contiguous blocks keep the GQA grouping)."""
+    nq, nkv, Ha, Hkva = H * d, Hkv * d, H // R, Hkv // R
+    return torch.cat([qkv[:, r * Ha * d:(r + 1) * Ha * d], qkv[:, nq + r * Hkva * d: nq + (r + 1) * Hkva * d],
+                      qkv[:, nq + nkv + r * Hkva * d: nq + nkv + (r + 1) * Hkva * d]], dim=1)
+
+
+def merge_head_slices(parts, H: int, Hkv: int, d: int) -> torch.Tensor:
+    """Inverse of head_slices over all ranks: per-rank [q_l | k_l | v_l] blocks -> [q | k | v] of all heads."""
+    R = len(parts)
+    qa, ka = (H // R) * d, (Hkv // R) * d
+    return torch.cat([p_[:, :qa] for p_ in parts] + [p_[:, qa:qa + ka] for p_ in parts] + [p_[:, qa + ka:] for p_ in parts], dim=1)
+
+
 def _gather_cols(local: torch.Tensor, R: int, grp) -> list:
     import torch.distributed as dist
     parts = [torch.empty_like(local) for _ in range(R)]
@@ -167,8 +182,7 @@ class _BlockFn(torch.autograd.Function):
             if hp is not None:
                 r, R, grp = hp
                 Ha, Hkva = H // R, Hkv // R
-                qkv = torch.cat([qkv[:, r * Ha * d:(r + 1) * Ha * d], qkv[:, nq + r * Hkva * d: nq + (r + 1) * Hkva * d],
-                                 qkv[:, nq + nkv + r * Hkva * d: nq + nkv + (r + 1) * Hkva * d]], dim=1)
+                qkv = head_slices(qkv, r, R, H, Hkv, d)
             packed = torch.empty(lib.gaot_attn_packed_bytes(B, S, Ha, Hkva, d), dtype=torch.uint8, device=dev)
             o = torch.empty(M, Ha * d, dtype=BF16, device=dev)
             o32 = torch.empty(M, Ha * d, dtype=torch.float32, device=dev)    # unrounded copy: the backward's D = rowsum(dO * O)
@@ -239,10 +253,7 @@ class _BlockFn(torch.autograd.Function):
                                                    _p(ws), wsb, _p(dqkv), dqkv.stride(0), _stream(dev)), "attn_fused_backward")
             del do, ws
             if hp is not None:                                                  # [dq_l | dk_l | dv_l] of every rank -> [dq | dk | dv]
-                parts = _gather_cols(dqkv, hp[1], hp[2])
-                qa, ka = Ha * d, Hkva * d
-                dqkv = torch.cat([p_[:, :qa] for p_ in parts] + [p_[:, qa:qa + ka] for p_ in parts] +
-                                 [p_[:, qa + ka:] for p_ in parts], dim=1)
+                dqkv = merge_head_slices(_gather_cols(dqkv, hp[1], hp[2]), H, Hkv, d)
             dh1 = _linear_bwd_x_raw(dqkv, wqkv, f32)
             dwqkv = torch.empty(nq + 2 * nkv, Hd, dtype=f32, device=dev)
             _linear_bwd_w_raw(dqkv, h1, dwqkv)

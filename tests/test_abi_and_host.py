@@ -88,3 +88,26 @@ def test_host_logic():
         G.MAGNOEncoder(3, 8, mc2)(bt, torch.rand(8, 3), torch.zeros(8, dtype=torch.long))
     with pytest.raises(ValueError):
         G.init_model(3, 1, "other")
+
+
+def test_head_parallel_column_bookkeeping():
+    """Sharded mode splits the attention core by heads (tblock.head_slices / merge_head_slices): slicing every rank's heads
+    out of [q | k | v] and merging the per-rank blocks back is the identity, with and without grouped kv heads; the
+    eligibility rule needs both head counts to divide by the world size."""
+    from gaot_3d_b200 import tblock
+    torch.manual_seed(0)
+    for H, Hkv, d, R in ((8, 8, 32, 2), (8, 8, 32, 8), (8, 4, 32, 4), (4, 2, 64, 2)):
+        qkv = torch.randn(17, (H + 2 * Hkv) * d)
+        parts = [tblock.head_slices(qkv, r, R, H, Hkv, d) for r in range(R)]
+        assert all(p.shape == (17, (H // R + 2 * (Hkv // R)) * d) and p.is_contiguous() for p in parts)
+        assert torch.equal(tblock.merge_head_slices(parts, H, Hkv, d), qkv)
+        # rank r's block holds exactly its q heads and the kv heads those q heads attend to
+        r = R - 1
+        Ha, g = H // R, H // Hkv
+        q_heads = range(r * Ha, (r + 1) * Ha)
+        kv_needed = sorted({h // g for h in q_heads})
+        assert kv_needed == list(range(r * (Hkv // R), (r + 1) * (Hkv // R)))
+    assert tblock._head_shard(8, 8) is None                   # off unless the sharded forward switches it on
+    import gaot_3d_b200 as G
+    with pytest.raises(ValueError):
+        G.set_node_mlp_mode("fast")
