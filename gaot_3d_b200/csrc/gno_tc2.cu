@@ -40,15 +40,6 @@ __device__ __forceinline__ __half2 tanh_h2(__half2 u) {
     asm("tanh.approx.f16x2 %0, %1;" : "=r"(r) : "r"(h2_as_u32(u)));
     return u32_as_h2(r);
 }
-// tanh-form GELU on a packed pair (see gelu_tanh_fast in gno_bf16.cu)
-__device__ __forceinline__ __half2 gelu_h2(__half2 x) {
-    const __half2 c1 = __float2half2_rn(0.0356774081f), c0 = __float2half2_rn(0.7978845608f), hf = __float2half2_rn(0.5f);
-    const __half2 x2 = __hmul2(x, x);
-    const __half2 u = __hmul2(x, __hfma2(x2, c1, c0));
-    const __half2 t = tanh_h2(u);
-    const __half2 hx = __hmul2(x, hf);
-    return __hfma2(hx, t, hx);
-}
 // gelu and its derivative from one tanh.  x*x is clamped so that |x| > 255 gives (x or 0, 1 or 0), not inf*0
 __device__ __forceinline__ void gelu_and_grad_h2(__half2 x, __half2& g, __half2& dg) {
     const __half2 c1 = __float2half2_rn(0.0356774081f), c0 = __float2half2_rn(0.7978845608f), hf = __float2half2_rn(0.5f);

@@ -23,13 +23,13 @@ constexpr int W2_B = NOUT * KP2 * 2;                 // 8704:  [16 x 272]
 constexpr int A0_B = TE * KP1 * 2;                   // 12288: [128 x 48]
 constexpr int ACT_B = TE * KP2 * 2;                  // 69632: [128 x 272]
 constexpr int F_W1 = 0, F_W2 = W1_B, F_GRP = 33792, F_GSTRIDE = A0_B + ACT_B;      // per stream: [A0 | ACT]
+static_assert(W1_B + W2_B <= F_GRP && F_GRP % 1024 == 0, "weight tiles must fit in front of the per-stream regions");
 constexpr int F_SMEM = F_GRP + FG * F_GSTRIDE;       // 197632
 // backward
 constexpr int BT = 256;
 constexpr int B_W1 = 0, B_W2 = W1_B, B_A0 = 33792, B_DY = B_A0 + A0_B, B_G = B_DY + TE * NOUT * 2, B_GP = B_G + ACT_B;
 constexpr int B_SMEM = B_GP + TE * HID * 2;          // 33792 + 12288 + 4096 + 69632 + 65536 = 185344
 constexpr int TM_DW2 = 256, TM_DW1 = 256 + 48;       // TMEM columns: work 0..255, dW2^T (3 x 16), dW1 (2 x 48)
-constexpr int N_PARAMS_MAX = HID * CIN + HID + 8 * HID + 8;
 }
 
 __device__ __forceinline__ uint32_t nm_h2u(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
