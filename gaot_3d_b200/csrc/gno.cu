@@ -80,8 +80,9 @@ int gaot_gno_forward_weighted(const float* y_pos, int64_t n_src, const float* x_
     if (rc) return rc;
     GAOT_CHECK_ARG(edge_w == nullptr || reduce == 1, "gno: per-edge weights go with reduce = sum (integral_transform.py:165)");
     a.edge_w = edge_w;
-    // the attentional variant runs on the FP32 kernels (the tensor-core kernels fold 1/count, not a per-edge weight)
-    if (precision == 0 || edge_w) return gno_forward_fp32(a, ws, ws_bytes, out, (cudaStream_t)stream);
+    // per-edge weights: FP32 kernels or the second-generation tensor-core kernels (the first generation has no weight path)
+    if (precision == 0) return gno_forward_fp32(a, ws, ws_bytes, out, (cudaStream_t)stream);
+    if (edge_w && !(use_gen2() && gno_forward_tc2_supported(a))) return gno_forward_fp32(a, ws, ws_bytes, out, (cudaStream_t)stream);
     if (precision == 1) {
         if (use_gen2() && gno_forward_tc2_supported(a)) return gno_forward_tc2(a, ws, ws_bytes, out, (cudaStream_t)stream);
         if (gno_forward_bf16_supported(a)) return gno_forward_bf16(a, ws, ws_bytes, out, (cudaStream_t)stream);
@@ -112,7 +113,8 @@ int gaot_gno_backward_weighted(const float* y_pos, int64_t n_src, const float* x
     GAOT_CHECK_ARG(edge_w != nullptr || d_edge_w == nullptr, "gno_backward: d_edge_w without edge_w");
     GAOT_CHECK_ARG(edge_w == nullptr || reduce == 1, "gno: per-edge weights go with reduce = sum");
     a.edge_w = edge_w; a.d_edge_w = d_edge_w;
-    if (edge_w) return gno_backward_fp32(a, d_out, ws, ws_bytes, d_params, d_f_y, (cudaStream_t)stream);
+    if (edge_w && !(precision == 1 && use_gen2() && gno_backward_tc2_supported(a)))
+        return gno_backward_fp32(a, d_out, ws, ws_bytes, d_params, d_f_y, (cudaStream_t)stream);
     // precision 1: tensor-core backward when the MLP fits its envelope, otherwise the FP32 recompute
     if (precision == 1 && use_gen2() && gno_backward_tc2_supported(a))
         return gno_backward_tc2(a, d_out, ws, ws_bytes, d_params, d_f_y, (cudaStream_t)stream);

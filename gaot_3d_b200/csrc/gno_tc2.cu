@@ -296,6 +296,7 @@ gno_fwd_tc2_kernel(const GnoArgs a, const Tc2Layout L, float* __restrict__ out, 
                 float v[32];
                 tc::tmem_ld32(tlane, v);
                 if (has_f) { tc::mbar_wait(&mbar_f[g], ph_f); ph_f ^= 1; }
+                const float ew = (a.edge_w && valid) ? a.edge_w[e0 + row] : 1.0f;
                 float* fr = F + row * FROW;
 #pragma unroll
                 for (int c = 0; c < 32; c += 4) {
@@ -304,6 +305,7 @@ gno_fwd_tc2_kernel(const GnoArgs a, const Tc2Layout L, float* __restrict__ out, 
                         const float4 f = *reinterpret_cast<const float4*>(fr + c);
                         o.x *= f.x; o.y *= f.y; o.z *= f.z; o.w *= f.w;
                     }
+                    o.x *= ew; o.y *= ew; o.z *= ew; o.w *= ew;       // attention weight of the edge (1 when there is none)
                     *reinterpret_cast<float4*>(fr + c) = o;
                 }
                 tc::fence_before_sync();
@@ -467,15 +469,21 @@ gno_bwd_tc2_kernel(const GnoArgs a, const Tc2BwdLayout L, const float* __restric
         *reinterpret_cast<uint4*>(A0 + 128 * 16 + row * 16) = c1;
     };
     // loads only (no arithmetic on the results: a consumer would stall the in-order warp on the load latency)
-    auto load_row = [&](int src, int qry, float (&c6)[6], int& rb, int& re) {
+    auto load_row = [&](int src, int qry, int e, float (&c6)[6], int& rb, int& re) {
         if (half == 0) {
             const float* py = a.y_pos + (size_t)src * 3;
             const float* px = a.x_pos + (size_t)qry * 3;
             c6[0] = py[0]; c6[1] = py[1]; c6[2] = py[2]; c6[3] = px[0]; c6[4] = px[1]; c6[5] = px[2];
         }
-        rb = a.rowptr[qry]; re = a.rowptr[qry + 1];
+        if (a.edge_w) { rb = __float_as_int(a.edge_w[e]); re = 0; }
+        else { rb = a.rowptr[qry]; re = a.rowptr[qry + 1]; }
     };
-    auto inv_count = [&](int rb, int re, bool valid) { return !valid ? 0.f : (a.reduce == 0 ? 1.0f / (float)(re - rb) : 1.0f); };
+    // the factor every edge gradient carries: 1/count (mean), 1 (sum), or the edge's attention weight (`rb` then holds its bits)
+    auto inv_count = [&](int rb, int re, bool valid) {
+        if (!valid) return 0.f;
+        if (a.edge_w) return __int_as_float(rb);
+        return a.reduce == 0 ? 1.0f / (float)(re - rb) : 1.0f;
+    };
 
     // ---- first tile of this CTA: synchronous staging; later tiles are staged by the software pipeline below ----
     int tile = blockIdx.x;
@@ -485,7 +493,7 @@ gno_bwd_tc2_kernel(const GnoArgs a, const Tc2BwdLayout L, const float* __restric
         const bool valid = row < min(T2E, a.E - tile * T2E);
         float c6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         int rb = 0, re = 1;
-        if (valid) { src = a.csr_src[tile * T2E + row]; qry = a.csr_qry[tile * T2E + row]; load_row(src, qry, c6, rb, re); }
+        if (valid) { src = a.csr_src[tile * T2E + row]; qry = a.csr_qry[tile * T2E + row]; load_row(src, qry, tile * T2E + row, c6, rb, re); }
         inv = inv_count(rb, re, valid);
         if (half == 0) write_a0(c6, valid);
     }
@@ -542,7 +550,7 @@ gno_bwd_tc2_kernel(const GnoArgs a, const Tc2BwdLayout L, const float* __restric
                 __syncwarp();
             }
             if (l == 0 && nvalid) { nsrc = a.csr_src[ntile * T2E + row]; nqry = a.csr_qry[ntile * T2E + row]; }
-            if (l == 1 && nvalid) load_row(nsrc, nqry, nc6, nrb, nre);
+            if (l == 1 && nvalid) load_row(nsrc, nqry, ntile * T2E + row, nc6, nrb, nre);
             if (l == (NL >= 3 ? NL - 2 : NL - 1)) {
                 // d_out rows of this tile (query-major CSR: neighbouring edges share them), issued one layer early
                 const float4* gp4 = reinterpret_cast<const float4*>(d_out + (size_t)qry * Cout + half * nc);
@@ -595,6 +603,12 @@ gno_bwd_tc2_kernel(const GnoArgs a, const Tc2BwdLayout L, const float* __restric
 
         // =============== output-side gradients (fp32) ===============
         {
+            if (a.d_edge_w && valid) {                  // d loss / d w_e = <d_out[q], k_e (* f_e)>: this thread's 16 of the 32 terms
+                float dot = 0.f;
+#pragma unroll
+                for (int c = 0; c < nc; ++c) dot = fmaf(gr[c] * kv[c], use_f_mul ? fr[c] : 1.0f, dot);
+                atomicAdd(a.d_edge_w + e0 + row, dot);
+            }
 #pragma unroll
             for (int c = 0; c < nc; ++c) gr[c] *= inv;
             if (use_f_mul) {
@@ -729,6 +743,7 @@ bool gno_backward_tc2_supported(const GnoArgs& a) {
 int gno_backward_tc2(const GnoArgs& a, const float* d_out, void* ws, size_t ws_bytes, float* d_params, float* d_f,
                      cudaStream_t st) {
     if (d_f) GAOT_CUDA(cudaMemsetAsync(d_f, 0, (size_t)a.n_src * a.c_f * sizeof(float), st));
+    if (a.d_edge_w && a.E > 0) GAOT_CUDA(cudaMemsetAsync(a.d_edge_w, 0, (size_t)a.E * sizeof(float), st));
     if (a.E == 0) {
         GAOT_CUDA(cudaMemsetAsync(d_params, 0, (size_t)a.n_params * sizeof(float), st));
         return GAOT_OK;

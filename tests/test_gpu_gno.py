@@ -292,3 +292,41 @@ def test_gno_attentional_transform(attention_type):
             assert float(params[n].grad.abs().max()) < 1e-12 and float(p.grad.abs().max()) < 1e-5
             continue
         close(p.grad, params[n].grad, rtol=1e-4, atol_rel=5e-5, what=f"d {n}")
+
+
+@pytest.mark.parametrize("attention_type", ["cosine", "dot_product"])
+def test_gno_attentional_transform_tensor_core(attention_type):
+    """The attentional variant on the second-generation tensor-core kernels (per-edge weight in the epilogue, d weight out
+    of the backward): rtol 2e-2 tier against the fp64 oracle, relative L2 like the other mixed-precision GNO tests."""
+    from gaot_3d_b200 import ops
+    from gaot_3d_b200.layers import IntegralTransform
+    torch.manual_seed(4)
+    phys, lat = synth.surface_cloud(6000, seed=7), synth.latent_grid((8, 8, 8))
+    ei = torch.from_numpy(og.radius_np(phys, lat, 0.25, workers=-1)[::-1].copy())
+    ypos, xpos = torch.from_numpy(phys), torch.from_numpy(lat)
+    it = IntegralTransform(channel_mlp_layers=[6, 64, 64, 32], use_attn=True, coord_dim=3, attention_type=attention_type).to(DEV)
+    f = torch.randn(ypos.shape[0], 32)
+    fd = f.to(DEV).requires_grad_(True)
+    prev = ops.get_gno_precision()
+    ops.set_gno_precision("bf16")
+    try:
+        out = it(ypos.to(DEV), xpos.to(DEV), ei.to(DEV), fd)
+        g = torch.randn(xpos.shape[0], 32)
+        out.backward(g.to(DEV))
+    finally:
+        ops.set_gno_precision(prev)
+    params = {n: p.detach().cpu().double().requires_grad_(True) for n, p in it.named_parameters()}
+    attn = dict(type=attention_type, coord_dim=3)
+    if attention_type == "dot_product":
+        attn.update(wq=params["query_proj.weight"], bq=params["query_proj.bias"], wk=params["key_proj.weight"], bk=params["key_proj.bias"])
+    fr = f.double().requires_grad_(True)
+    ref = ogno.integral_transform(ypos.double(), xpos.double(), ei, fr, [params[f"channel_mlp.fcs.{i}.weight"] for i in range(3)],
+                                  [params[f"channel_mlp.fcs.{i}.bias"] for i in range(3)], attn=attn)
+    ref.backward(g.double())
+    rl2 = lambda a, b: ((a.detach().double().cpu() - b).norm() / b.norm().clamp(min=1e-30)).item()
+    assert rl2(out, ref) < 1e-2, ("out", rl2(out, ref))
+    assert rl2(fd.grad, fr.grad) < 2e-2, ("d_f", rl2(fd.grad, fr.grad))
+    for n, p in it.named_parameters():
+        if n == "key_proj.bias":
+            continue                                            # identically zero (softmax shift invariance)
+        assert rl2(p.grad, params[n].grad) < 2e-2, (n, rl2(p.grad, params[n].grad))
