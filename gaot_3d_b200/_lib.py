@@ -86,7 +86,6 @@ _SIGS = {
                                          P, c_size_t, P, c_int64, P]),
     "gaot_radius_host": (c_int, [P, c_int64, P, c_int64, c_double, c_int, P, P, POINTER(c_int64)]),
     "gaot_knn_host": (c_int, [P, c_int64, P, c_int64, c_int, P, P, POINTER(c_int64)]),
-    "gaot_tc_probe": (c_int, [P, P, P, c_int, c_int, c_int, P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)

@@ -419,7 +419,9 @@ gemm2_kernel(const GemmArgs g, int tiles_n, int total_tiles) {
 
 template <bool B_MN>
 static int launch_gemm2(const GemmArgs& g, cudaStream_t st) {
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {};      // the attribute is per device: one flag per device ordinal
+    int dev_ = 0; cudaGetDevice(&dev_);
+    bool& attr_done = attr_done_dev[dev_ & 63];
     auto kern = gemm2_kernel<B_MN>;
     if (!attr_done) {
         GAOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dn2::SMEM_BYTES));
@@ -666,7 +668,9 @@ gemm3_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap tmA, const __
 // returns GAOT_ERR_UNSUPPORTED when the operands do not meet the TMA constraints (caller falls back to the register-staged kernels)
 template <bool A_MN, bool B_MN>
 static int launch_gemm3(const GemmArgs& g, int splits, cudaStream_t st) {
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {};      // the attribute is per device: one flag per device ordinal
+    int dev_ = 0; cudaGetDevice(&dev_);
+    bool& attr_done = attr_done_dev[dev_ & 63];
     auto kern = gemm3_kernel<A_MN, B_MN>;
     if (((uintptr_t)g.A | (uintptr_t)g.B) & 15) return GAOT_ERR_UNSUPPORTED;
     CUtensorMap tmA, tmB;
@@ -722,7 +726,9 @@ static int pick_splits(int64_t M, int64_t N, int64_t K) {
 
 template <typename TA, typename TB, bool A_MN, bool B_MN>
 static int launch_gemm(const GemmArgs& g, int splits, cudaStream_t st) {
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {};      // the attribute is per device: one flag per device ordinal
+    int dev_ = 0; cudaGetDevice(&dev_);
+    bool& attr_done = attr_done_dev[dev_ & 63];
     auto kern = gemm_tc_kernel<TA, TB, A_MN, B_MN>;
     if (!attr_done) {
         GAOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dn::SMEM_BYTES));

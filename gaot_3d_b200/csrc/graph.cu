@@ -363,10 +363,22 @@ mask_emit_kernel(const int64_t* __restrict__ r0, const int64_t* __restrict__ r1,
 }
 
 __global__ void __launch_bounds__(256)
-csr_keys_kernel(const int64_t* __restrict__ qry, int64_t n, uint64_t* __restrict__ keys, int32_t* __restrict__ cnt) {
+csr_keys_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ qry, int64_t n, int64_t n_src, int64_t nq,
+                uint64_t* __restrict__ keys, int32_t* __restrict__ cnt, int32_t* __restrict__ status /* may be NULL: trusted */) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int64_t q = qry[i];
+    if (status) {
+        // edge lists that come from outside (precomputed edges, magno.py:506-516) are range-checked once here: every
+        // later kernel gathers rows by these indices.  bit 0: query index out of [0,nq); bit 1: source index out of
+        // [0,n_src); bit 2: claimed query-sorted but not monotone
+        int bad = 0;
+        if (q < 0 || q >= nq) bad |= 1;
+        const int64_t s = src[i];
+        if (s < 0 || s >= n_src) bad |= 2;
+        if (!keys && i > 0 && qry[i - 1] > q) bad |= 4;
+        if (bad) { atomicOr(status, bad); if (bad & 1) return; }
+    }
     if (keys) keys[i] = ((uint64_t)q << 32) | (uint64_t)(uint32_t)i;
     atomicAdd(&cnt[q], 1);
 }
@@ -560,7 +572,7 @@ int gaot_edge_mask(const int64_t* row0, const int64_t* row1, int64_t E, double p
 size_t gaot_csr_workspace_bytes(int64_t E, int64_t nq) {
     if (E < 1) E = 1;
     return 2 * align_up((size_t)E * sizeof(uint64_t)) + align_up(sort_workspace_bytes(E)) +
-           align_up(scan_workspace_bytes(nq + 1)) + 1024;
+           align_up(scan_workspace_bytes(nq + 1)) + align_up(sizeof(int32_t)) + 1024;
 }
 
 int gaot_csr_from_edges(const int64_t* src, const int64_t* qry, int64_t E, int64_t n_src, int64_t nq,
@@ -571,16 +583,30 @@ int gaot_csr_from_edges(const int64_t* src, const int64_t* qry, int64_t E, int64
     GAOT_CHECK_ARG(nq >= 0 && nq < ((int64_t)1 << 31) - 1 && n_src < ((int64_t)1 << 31), "csr: bad sizes");
     GAOT_CUDA(cudaMemsetAsync(rowptr, 0, (size_t)(nq + 1) * sizeof(int32_t), st));
     if (E == 0) return GAOT_OK;
-    const bool sorted = (flags & 1) != 0;
+    const bool sorted = (flags & 1) != 0, validate = (flags & 2) != 0;
     Arena ar(ws, ws_bytes);
     uint64_t* keys = ar.take<uint64_t>((size_t)E);
     uint64_t* tmp = ar.take<uint64_t>((size_t)E);
     const size_t sb = sort_workspace_bytes(E), cb = scan_workspace_bytes(nq + 1);
     char* sort_ws = ar.take<char>(sb);
     char* scan_ws = ar.take<char>(cb);
+    int32_t* status = ar.take<int32_t>(1);
     if (!ar.ok()) { set_error("csr: workspace too small"); return GAOT_ERR_WORKSPACE; }
-    csr_keys_kernel<<<nblk(E, 256), 256, 0, st>>>(qry, E, sorted ? nullptr : keys, rowptr);
+    if (validate) GAOT_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
+    csr_keys_kernel<<<nblk(E, 256), 256, 0, st>>>(src, qry, E, n_src, nq, sorted ? nullptr : keys, rowptr,
+                                                  validate ? status : nullptr);
     GAOT_LAUNCH_CHECK();
+    if (validate) {      // one 4-byte read-back per externally supplied edge list, before anything gathers by its indices
+        int32_t h = 0;
+        GAOT_CUDA(cudaMemcpyAsync(&h, status, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        GAOT_CUDA(cudaStreamSynchronize(st));
+        if (h) {
+            set_error("csr: edge_index is invalid for n_src=%lld, nq=%lld:%s%s%s", (long long)n_src, (long long)nq,
+                      (h & 1) ? " query index (row 1) out of range;" : "", (h & 2) ? " source index (row 0) out of range;" : "",
+                      (h & 4) ? " marked query-sorted but row 1 is not monotone;" : "");
+            return GAOT_ERR_INVALID;
+        }
+    }
     int rc = exclusive_scan_i32(rowptr, rowptr, nq, true, scan_ws, cb, st);
     if (rc) return rc;
     if (!sorted) {

@@ -55,6 +55,8 @@ def _per_example(fn, x, y, batch_x, batch_y):
     B = _num_examples(batch_x, batch_y)
     if B == 1:
         return fn(x, y)
+    if batch_x is None or batch_y is None:
+        raise ValueError("batched neighbour search needs BOTH batch vectors (got one None with more than one example)")
     sx, sy = _example_slices(batch_x, x.shape[0], B), _example_slices(batch_y, y.shape[0], B)
     rows, cols = [], []
     for (x0, x1), (y0, y1) in zip(sx, sy):
@@ -78,6 +80,7 @@ def knn_graph(x, y, k, batch_x=None, batch_y=None):
 
 def _tag(ei: torch.Tensor, query_sorted: bool) -> torch.Tensor:
     ei._gaot_query_sorted = query_sorted     # side-band hint: CSR build can skip its sort
+    ei._gaot_trusted = True                  # built by this package's kernels: ops.csr_of skips the index validation
     return ei
 
 
@@ -130,7 +133,10 @@ def get_neighbor_strategy(neighbor_strategy: str, phys_pos: torch.Tensor, batch_
               float(radius), int(k_neighbors))
 
 
-_mask_calls = [0]
+# Philox stream position of the edge-dropout masks: one running counter per torch seed, advanced by the number of
+# counter values a call consumes (ceil(E/4)), so the masks of different calls (encoder / decoder, scales, samples) never
+# share random words; torch.manual_seed() restarts the stream (reproducible runs).
+_mask_stream = {"seed": None, "offset": 0}
 
 
 def apply_neighbor_sampling(edge_index: torch.Tensor, num_query_nodes: int, device=None,
@@ -149,11 +155,14 @@ def apply_neighbor_sampling(edge_index: torch.Tensor, num_query_nodes: int, devi
         if sample_ratio >= 1.0 or not training:
             return edge_index
         seed = int(torch.initial_seed())
-        _mask_calls[0] += 1
-        r0, r1 = ops.edge_mask(edge_index[0], edge_index[1], 1.0 - float(sample_ratio), seed,
-                               offset=_mask_calls[0] * ((E + 3) // 4))
+        if _mask_stream["seed"] != seed:
+            _mask_stream["seed"], _mask_stream["offset"] = seed, 0
+        offset = _mask_stream["offset"]
+        _mask_stream["offset"] = (offset + (E + 3) // 4) & (2 ** 64 - 1)
+        r0, r1 = ops.edge_mask(edge_index[0], edge_index[1], 1.0 - float(sample_ratio), seed, offset=offset)
         out = torch.stack([r0, r1])
         out._gaot_query_sorted = bool(getattr(edge_index, "_gaot_query_sorted", False))
+        out._gaot_trusted = bool(getattr(edge_index, "_gaot_trusted", False))
         return out
     if sampling_strategy == "max_neighbors":
         if max_neighbors is None:

@@ -225,7 +225,10 @@ class Csr:
         return int(self.src.numel())
 
 
-def build_csr(src: torch.Tensor, qry: torch.Tensor, n_src: int, nq: int, query_sorted: bool = False) -> Csr:
+def build_csr(src: torch.Tensor, qry: torch.Tensor, n_src: int, nq: int, query_sorted: bool = False,
+              validate: bool = True) -> Csr:
+    """`validate` (default): indices are range-checked on the device (and the `query_sorted` claim verified) before any
+    kernel gathers by them; a bad edge list raises ValueError.  Graphs this package built itself skip the check."""
     _need_cuda(src, qry)
     src = src.to(torch.long).contiguous()
     qry = qry.to(torch.long).contiguous()
@@ -238,7 +241,7 @@ def build_csr(src: torch.Tensor, qry: torch.Tensor, n_src: int, nq: int, query_s
     wsb = lib.gaot_csr_workspace_bytes(E, nq)
     ws = _ws(wsb, dev)
     with torch.cuda.device(dev):
-        check(lib.gaot_csr_from_edges(_p(src), _p(qry), E, int(n_src), int(nq), 1 if query_sorted else 0,
+        check(lib.gaot_csr_from_edges(_p(src), _p(qry), E, int(n_src), int(nq), (1 if query_sorted else 0) | (2 if validate else 0),
                                       _p(ws), wsb, _p(rowptr), _p(cs), _p(cq), _p(pm), _stream(dev)), "csr_from_edges")
     return Csr(rowptr, cs, cq, pm, int(n_src), int(nq))
 
@@ -249,7 +252,10 @@ def csr_of(edge_index: torch.Tensor, n_src: int, nq: int) -> Csr:
     cache = getattr(edge_index, "_gaot_csr", None)
     if cache is not None and cache.n_src == n_src and cache.nq == nq and cache.E == edge_index.shape[1]:
         return cache
-    csr = build_csr(edge_index[0], edge_index[1], n_src, nq, bool(getattr(edge_index, "_gaot_query_sorted", False)))
+    # `_gaot_trusted` is set by graph._tag on edge lists produced by this package's own search / coalesce / mask kernels;
+    # anything else (precomputed edges from dataset files, reference magno.py:506-516) is validated once here
+    csr = build_csr(edge_index[0], edge_index[1], n_src, nq, bool(getattr(edge_index, "_gaot_query_sorted", False)),
+                    validate=not bool(getattr(edge_index, "_gaot_trusted", False)))
     try:
         edge_index._gaot_csr = csr
     except Exception:

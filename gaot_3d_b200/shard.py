@@ -136,6 +136,16 @@ def sharded_forward(model, batch_local, tokens_pos, n_total: int, group=None, en
     enc, dec = model.encoder, model.decoder
     if len(enc.scales) != 1 or not enc.use_gno:
         raise NotImplementedError("sharded path: single scale with the GNO enabled")
+    # options whose sharded form needs a collective this path does not have (silently wrong otherwise)
+    if enc.gno.use_attn or dec.gno.use_attn:
+        raise NotImplementedError("sharded path: use_attn needs a global segment softmax across the ranks")
+    if enc.sampling_strategy is not None:
+        raise NotImplementedError("sharded path: sampling_strategy must be None")
+    if getattr(batch_local, "num_graphs", 1) != 1:
+        raise NotImplementedError("sharded path: one example per step (num_graphs == 1)")
+    for side in (enc, dec):
+        if side.use_geoembed and side.geoembed.method != "statistical":
+            raise NotImplementedError("sharded path: geometric embedding method must be 'statistical'")
     from .layers.magno import _apply_node_mlp
     dev = batch_local.pos.device
     lat = tokens_pos.to(dev)

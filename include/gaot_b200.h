@@ -100,7 +100,10 @@ int gaot_edge_mask(const int64_t* row0, const int64_t* row1, int64_t E_in, doubl
  */
 size_t gaot_csr_workspace_bytes(int64_t E, int64_t nq);
 int gaot_csr_from_edges(const int64_t* src, const int64_t* qry, int64_t E, int64_t n_src, int64_t nq,
-                        int flags /* bit0: edges already grouped by ascending qry (trusted hint) */,
+                        int flags /* bit0: edges already grouped by ascending qry; bit1: VALIDATE -- range-check
+                                     every index (0 <= qry < nq, 0 <= src < n_src) and the bit0 claim in the same
+                                     pass; one 4-byte read-back; GAOT_ERR_INVALID instead of an out-of-bounds
+                                     access (the reference's torch indexing raises IndexError there) */,
                         void* ws, size_t ws_bytes, int32_t* rowptr, int32_t* csr_src,
                         int32_t* csr_qry, int32_t* perm, void* stream);
 
@@ -290,10 +293,6 @@ int gaot_radius_host(const float* x_host, int64_t nx, const float* y_host, int64
                      int64_t* out_y_host, int64_t* out_x_host, int64_t* E_host);
 int gaot_knn_host(const float* x_host, int64_t nx, const float* y_host, int64_t ny, int k,
                   int64_t* out_y_host, int64_t* out_x_host, int64_t* E_host);
-
-/* tcgen05 self-test (layout / descriptor probe used by tests/test_tcgen05_probe.py):
- * D[128,N] = A[128,K] * B[N,K]^T in bf16 with fp32 accumulate; variant selects operand majors. */
-int gaot_tc_probe(const float* A, const float* B, float* D, int N, int K, int variant, void* stream);
 
 #ifdef __cplusplus
 }

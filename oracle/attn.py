@@ -46,12 +46,12 @@ def attention_core(q, k, v, num_heads, num_kv_heads, rope: bool, dtype=torch.flo
         k = k.repeat_interleave(rep, dim=1)
         v = v.repeat_interleave(rep, dim=1)
     if rope:                                                        # attn.py:118-120
-        re = RotaryEmbedding(d).to(dtype)
+        re = RotaryEmbedding(d).to(device=q.device, dtype=dtype)
         q = re.rotate_queries_or_keys(q)
         k = re.rotate_queries_or_keys(k)
     s = (q @ k.transpose(-1, -2)) / math.sqrt(d)                    # SDPA default scale
     p = torch.softmax(s, dim=-1)
     if dropout_p > 0.0:                                             # attn.py:122-126 (dropout inside SDPA)
-        p = p * dropout_keep(B, num_heads, S, dropout_p, seed).to(p.dtype) / (1.0 - dropout_p)
+        p = p * dropout_keep(B, num_heads, S, dropout_p, seed).to(device=p.device, dtype=p.dtype) / (1.0 - dropout_p)
     o = p @ v
     return o.transpose(1, 2).contiguous().view(B, S, HD)            # attn.py:128

@@ -14,14 +14,14 @@ import torch.nn.functional as F
 
 def scatter_mean(src, index, dim_size):
     """reference scatter_native.py:23-31 -- scatter_add_ then / bincount.clamp(min=1)."""
-    out = torch.zeros((dim_size,) + tuple(src.shape[1:]), dtype=src.dtype)
+    out = torch.zeros((dim_size,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
     out.index_add_(0, index, src)
     cnt = torch.bincount(index, minlength=dim_size).to(src.dtype)
     return out / cnt.clamp(min=1).view([-1] + [1] * (src.dim() - 1))
 
 
 def scatter_sum(src, index, dim_size):
-    out = torch.zeros((dim_size,) + tuple(src.shape[1:]), dtype=src.dtype)
+    out = torch.zeros((dim_size,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
     return out.index_add_(0, index, src)
 
 
@@ -37,7 +37,7 @@ def mlp_forward(x, weights, biases):
 
 def segment_softmax(scores, index, dim_size):
     """IntegralTransform._segment_softmax_pyg, reference integral_transform.py:68-78."""
-    smax = torch.zeros(dim_size, dtype=scores.dtype).scatter_reduce(0, index, scores, reduce="amax", include_self=False)
+    smax = torch.zeros(dim_size, dtype=scores.dtype, device=scores.device).scatter_reduce(0, index, scores, reduce="amax", include_self=False)
     ex = torch.exp(scores - smax[index])
     den = torch.clamp(scatter_sum(ex, index, dim_size), min=torch.finfo(ex.dtype).tiny)
     return ex / den[index]
@@ -52,7 +52,7 @@ def integral_transform(y_pos, x_pos, edge_index, f_y, weights, biases, transform
     """
     nq = x_pos.shape[0]
     if edge_index.shape[1] == 0:                                   # :107-112
-        return torch.zeros(nq, weights[-1].shape[0], dtype=weights[-1].dtype)
+        return torch.zeros(nq, weights[-1].shape[0], dtype=weights[-1].dtype, device=x_pos.device)
     src, qry = edge_index[0].long(), edge_index[1].long()          # :114-115
     rep, slf = y_pos[src], x_pos[qry]                              # :117-118
     inf = f_y[src] if f_y is not None else None                    # :120-123

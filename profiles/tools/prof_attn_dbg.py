@@ -1,5 +1,5 @@
 """Dev helper (GPU box): time the attention forward/backward kernels under a list of GAOT_ATTN_DEBUG values.
-usage: python tests/prof_attn_dbg.py 0 1 2 ...   (debug bits skip parts of the kernels: results are then WRONG, timing only)"""
+usage: python profiles/tools/prof_attn_dbg.py 0 1 2 ...   (debug bits skip parts of the kernels: results are then WRONG, timing only)"""
 import ctypes
 import os
 import sys

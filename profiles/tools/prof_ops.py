@@ -1,5 +1,5 @@
 """Standalone op runner for ncu / quick timing on the GPU box (not a pytest).
-usage: python tests/prof_ops.py attn|gno|graph [reps]"""
+usage: python profiles/tools/prof_ops.py attn|gno|graph [reps]"""
 import sys
 import time
 

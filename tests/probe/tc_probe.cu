@@ -1,9 +1,17 @@
-// tc_probe.cu -- single-CTA tcgen05 GEMM used by tests/test_tcgen05_probe.py to pin the
+// tc_probe.cu -- TEST INFRASTRUCTURE (built into tests/probe/libgaot_tcprobe.so, NOT part of libgaot_b200.so):
+// single-CTA tcgen05 GEMM used by tests/test_gpu_tc_probe.py to pin the
 // shared-memory descriptor conventions of tc05.cuh on real hardware:
 //   D[128,N] = A * B  (bf16 operands, fp32 accumulate in TMEM), for every combination of
 //   K-major / MN-major A and B operands built from the library's chunk-major tile format.
+#include <cstdarg>
 #include "common.cuh"
 #include "tc05.cuh"
+
+// standalone: the two hooks of common.cuh that the product library defines in abi.cu
+namespace gaot {
+void set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vfprintf(stderr, fmt, ap); va_end(ap); fputc('\n', stderr); }
+void count_launch(int) {}
+}  // namespace gaot
 
 namespace gaot {
 

@@ -145,3 +145,139 @@ def test_attention_full_size_properties():
     dirderiv = (kd.grad * u).sum().item()                     # d loss / d eps for k_j -> k_j + eps u ... per query q_i . u shifts row i uniformly
     ref_scale = (kd.grad.abs().sum() * u.abs().max()).item()
     assert abs(dirderiv) <= 2e-2 * ref_scale
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# Full-size parity against the ORACLE ("checked against themselves, not the oracle").  Two forms:
+#  (i)  the oracle's arithmetic in fp64 on the CPU for a random subset of the queries (all their edges / all keys);
+#  (ii) the oracle's own torch code executed in fp64 on the CUDA device over the WHOLE problem (5.9 M edges; all 16384
+#       query rows of some heads) -- same functions (oracle.gno.integral_transform, oracle.attn.attention_core), torch's
+#       fp64 kernels only make the full size finish in seconds.
+def _gno_setup(cloud, enc):
+    from gaot_3d_b200 import ops
+    from gaot_3d_b200.graph import get_neighbor_strategy
+    phys, lat, P, L = cloud
+    torch.manual_seed(3)
+    if enc:      # encoder radius graph: 1.08 M edges capped at 32 per latent token, 4-layer MLP
+        ei = get_neighbor_strategy("radius", P, None, L, None, R, 1, False)
+        ypos, xpos, layers = P, L, [6, 64, 64, 64, 32]
+    else:        # decoder radius graph: 5.9 M edges, 3-layer MLP
+        ei = get_neighbor_strategy("radius", P, None, L, None, R, 1, True)
+        ypos, xpos, layers = L, P, [6, 64, 64, 32]
+    nl = len(layers) - 1
+    ws = [torch.randn(layers[i + 1], layers[i], device=DEV) / layers[i] ** 0.5 for i in range(nl)]
+    bs = [torch.randn(layers[i + 1], device=DEV) * 0.1 for i in range(nl)]
+    f = torch.randn(ypos.shape[0], 32, device=DEV)
+    csr = ops.csr_of(ei, ypos.shape[0], xpos.shape[0])
+    return ei, ypos, xpos, ws, bs, f, csr
+
+
+def _rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm().clamp(min=1e-30)).item(), ((a - b).abs().max() / b.abs().max().clamp(min=1e-30)).item()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("enc", [False, True], ids=["decoder5.9M", "encoder1.1M"])
+def test_gno_full_size_vs_oracle(cloud, precision, enc):
+    from gaot_3d_b200 import ops
+    from oracle import gno as ogno
+    ei, ypos, xpos, ws, bs, f, csr = _gno_setup(cloud, enc)
+    nq = xpos.shape[0]
+    # ---- ours: forward, and a backward whose upstream gradient is non-zero on a random query subset only
+    rng = np.random.default_rng(5)
+    cnt = torch.bincount(ei[1], minlength=nq).cpu().numpy()
+    sub = np.unique(np.concatenate([rng.choice(nq, 400, replace=False), rng.choice(np.nonzero(cnt == cnt.max())[0], 16)]))
+    g_sub = torch.randn(len(sub), 32, device=DEV)
+    d_out = torch.zeros(nq, 32, device=DEV)
+    d_out[torch.from_numpy(sub).to(DEV)] = g_sub
+    wd = [w.clone().requires_grad_(True) for w in ws]
+    bd = [b.clone().requires_grad_(True) for b in bs]
+    fd = f.clone().requires_grad_(True)
+    out = ops.gno(ypos, xpos, fd, csr, wd, bd, precision=precision)
+    out.backward(d_out)
+    tol_l2, tol_mx = (2e-6, 1e-5) if precision == "fp32" else (1e-2, 2e-2)
+    gtol = 1e-4 if precision == "fp32" else 2e-2
+
+    # ---- (i) CPU fp64 oracle on the subset: its edges, re-indexed queries
+    rowptr, src = csr.rowptr.cpu().numpy(), csr.src.cpu().numpy()
+    e_src = np.concatenate([src[rowptr[q]:rowptr[q + 1]] for q in sub])
+    e_qry = np.concatenate([np.full(rowptr[q + 1] - rowptr[q], i) for i, q in enumerate(sub)])
+    ei_sub = torch.from_numpy(np.stack([e_src, e_qry]).astype(np.int64))
+    w64 = [w.detach().cpu().double().requires_grad_(True) for w in ws]
+    b64 = [b.detach().cpu().double().requires_grad_(True) for b in bs]
+    f64 = f.detach().cpu().double().requires_grad_(True)
+    ref = ogno.integral_transform(ypos.cpu().double(), xpos.cpu().double()[sub], ei_sub, f64, w64, b64)
+    l2, mx = _rel(out.detach().cpu()[sub], ref.detach())
+    assert l2 < tol_l2 and mx < tol_mx, f"subset forward vs CPU fp64 oracle: rel l2 {l2:.3e}, rel max {mx:.3e}"
+    ref.backward(g_sub.cpu().double())
+    for name, a, b_ in [("d f_y", fd.grad, f64.grad)] + [(f"dW{i}", wd[i].grad, w64[i].grad) for i in range(len(ws))] + \
+                       [(f"db{i}", bd[i].grad, b64[i].grad) for i in range(len(bs))]:
+        l2, mx = _rel(a.detach().cpu(), b_)
+        assert l2 < gtol, f"subset backward {name} vs CPU fp64 oracle: rel l2 {l2:.3e}"
+
+    # ---- (ii) the oracle's code in fp64 on the device over the whole graph
+    w64 = [w.detach().double().requires_grad_(True) for w in ws]
+    b64 = [b.detach().double().requires_grad_(True) for b in bs]
+    f64 = f.detach().double().requires_grad_(True)
+    ref = ogno.integral_transform(ypos.double(), xpos.double(), ei, f64, w64, b64)
+    l2, mx = _rel(out.detach(), ref.detach())
+    assert l2 < tol_l2 and mx < tol_mx, f"full forward vs fp64 oracle: rel l2 {l2:.3e}, rel max {mx:.3e}"
+    g_full = torch.randn(nq, 32, device=DEV)
+    for t in (fd, *wd, *bd):
+        t.grad = None
+    out2 = ops.gno(ypos, xpos, fd, csr, wd, bd, precision=precision)
+    out2.backward(g_full)
+    ref.backward(g_full.double())
+    for name, a, b_ in [("d f_y", fd.grad, f64.grad)] + [(f"dW{i}", wd[i].grad, w64[i].grad) for i in range(len(ws))] + \
+                       [(f"db{i}", bd[i].grad, b64[i].grad) for i in range(len(bs))]:
+        l2, mx = _rel(a.detach(), b_)
+        assert l2 < gtol, f"full backward {name} vs fp64 oracle: rel l2 {l2:.3e}"
+
+
+def test_attention_full_size_vs_oracle():
+    """S = 16384, H = 8, d = 32 (the transformer of every BASELINE config), RoPE on.  (i) 256 random query rows of every
+    head on the CPU in fp64 against all 16384 keys: output and dQ (a query row's dQ needs only that row's probabilities);
+    (ii) heads 0 and 5 completely (all rows; dQ, dK, dV) with the oracle's attention_core in fp64 on the device."""
+    from gaot_3d_b200 import ops
+    from gaot_3d_b200.layers.attn import RotaryEmbedding
+    from oracle import attn as oattn
+    from oracle.rope import RotaryEmbedding as ORope
+    import math
+    torch.manual_seed(1)
+    B, S, H, d = 1, 16384, 8, 32
+    q, k, v = (torch.randn(B, S, H * d, device=DEV) for _ in range(3))
+    go = torch.randn(B, S, H * d, device=DEV)
+    qd, kd, vd = (t.clone().requires_grad_(True) for t in (q, k, v))
+    freqs = RotaryEmbedding(d).freqs.to(DEV)
+    out = ops.attention(qd, kd, vd, H, H, rope_freqs=freqs)
+    out.backward(go)
+    # ---- (i) CPU fp64, random rows of every head
+    rows = torch.from_numpy(np.sort(np.random.default_rng(2).choice(S, 256, replace=False)))
+    rope = ORope(d).double()
+    to_h = lambda t: t.detach().cpu().double().view(S, H, d).transpose(0, 1)             # [H, S, d]
+    qh, kh, vh, gh = to_h(q), to_h(k), to_h(v), to_h(go)
+    qr, kr = rope.rotate_queries_or_keys(qh), rope.rotate_queries_or_keys(kh)
+    qs = qr[:, rows].clone().requires_grad_(True)                                      # [H, 256, d] rotated query rows
+    p = torch.softmax(qs @ kr.transpose(-1, -2) / math.sqrt(d), dim=-1)
+    o_ref = p @ vh
+    o_ref.backward(gh[:, rows])
+    o_ours = to_h(out)[:, rows]
+    l2, mx = _rel(o_ours, o_ref.detach())
+    assert l2 < 1e-2 and mx < 2e-2, f"subset rows forward: rel l2 {l2:.3e}, rel max {mx:.3e}"
+    # dQ of the un-rotated q: rotate ours forward (RoPE is orthogonal: d q = R^T d q_rot  <=>  R d q = d q_rot)
+    dq_rot_ours = rope.rotate_queries_or_keys(to_h(qd.grad))[:, rows]
+    l2, mx = _rel(dq_rot_ours, qs.grad)
+    assert l2 < 1e-2 and mx < 2e-2, f"subset rows dQ: rel l2 {l2:.3e}, rel max {mx:.3e}"
+    # ---- (ii) two whole heads with the oracle's code in fp64 on the device
+    for h in (0, 5):
+        sl = slice(h * d, (h + 1) * d)
+        q1, k1, v1 = (t[:, :, sl].double().clone().requires_grad_(True) for t in (q, k, v))
+        ref = oattn.attention_core(q1, k1, v1, 1, 1, True, dtype=torch.float64)
+        ref.backward(go[:, :, sl].double())
+        for name, a, b_ in (("out", out[:, :, sl], ref), ("dq", qd.grad[:, :, sl], q1.grad), ("dk", kd.grad[:, :, sl], k1.grad),
+                            ("dv", vd.grad[:, :, sl], v1.grad)):
+            l2, mx = _rel(a.detach(), b_.detach())
+            assert l2 < 1e-2 and mx < 2e-2, f"head {h} {name}: rel l2 {l2:.3e}, rel max {mx:.3e}"
+        del q1, k1, v1, ref
+        torch.cuda.empty_cache()

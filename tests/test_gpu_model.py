@@ -39,36 +39,13 @@ def test_model_golden(tag):
     ref = g["out"]
     err = (y.cpu() - ref).abs().max().item()
     assert err < 2e-2 * ref.abs().max().item(), f"{tag}: max abs err {err:.3e} vs max |ref| {ref.abs().max().item():.3e}"
-    # training step: gradients flow to every trainable parameter and match the oracle's autograd
-    m.train()
-    y = m(batch, tokens_pos=g["tokens_pos"].to(DEV))
-    y.pow(2).mean().backward()
-    missing = [n for n, p in m.named_parameters() if p.requires_grad and p.grad is None]
-    assert not missing, missing
-    sd = {k: v.float().clone().requires_grad_(v.dtype.is_floating_point and "freqs" not in k and k != "latent_tokens")
-          for k, v in g["state"].items()}
+    # training step: gradients flow to every trainable parameter; each tensor is held to rtol 2e-2 (relative L2) against
+    # the bf16-operand yardstick of oracle.model (q/k projections included -- no widened bars), see
+    # tests/test_gpu_model_variants.py::check_against_oracle
+    from tests.test_gpu_model_variants import check_against_oracle
     es, ds = G.parse_neighbor_strategy(g["strategy"])
     cfg = dict(latent_tokens=tuple(g["latent_tokens"]), patch_size=2, lifting_channels=32, radius=g["radius"], k=g["k"],
                enc_strategy=es, dec_strategy=ds, use_geoembed=g["use_geoembed"], num_layers=3, num_heads=4,
                num_kv_heads=m.processor.encoder_layers[0].attn.num_kv_heads, norm_eps=1e-6, positional_embedding="rope")
-
-    orig = dict(sd)
-    yo = omodel.gaot3d_forward(orig, cfg, g["pos"], [g["pos"], g["c"]], latent_pos=g["tokens_pos"], keep_graph=True)
-    yo.pow(2).mean().backward()
-    bad, report = [], []
-    for n, p in m.named_parameters():
-        if not p.requires_grad:
-            continue
-        ref_g = orig[n].grad
-        rel = ((p.grad.cpu() - ref_g).norm() / ref_g.norm().clamp(min=1e-12)).item()
-        cos = torch.nn.functional.cosine_similarity(p.grad.cpu().flatten().double(), ref_g.flatten().double(), dim=0).item()
-        # q/k projection gradients are differences of nearly cancelling softmax terms (dS = P*(dP - D)): BF16 operand
-        # rounding is relatively larger there (op-level dq/dk parity is pinned at 1e-2 in test_gpu_attn.py); they must
-        # still point the same way
-        qk = ".q_proj." in n or ".k_proj." in n
-        tol = 0.25 if qk else 5e-2
-        report.append(f"{n}: rel l2 {rel:.3e} cos {cos:.5f}")
-        if rel >= tol or cos < (0.97 if qk else 0.998):
-            bad.append(report[-1])
-    print("\n".join(report))
-    assert not bad, f"{tag} gradient parity: " + "; ".join(bad)
+    check_against_oracle(m, lambda: m(batch, tokens_pos=g["tokens_pos"].to(DEV)),
+                         dict(pos=g["pos"], feats=[g["pos"], g["c"]], latent_pos=g["tokens_pos"]), cfg, f"golden {tag}")

@@ -57,10 +57,26 @@ def test_fused_block_vs_oracle(B, S, hidden, heads, kv, ffn, skip, rope):
     for n, p in blk.named_parameters():
         if p.requires_grad:
             checks.append((n, p.grad, sd["b." + n].grad))
+    # bf16-operand yardstick (oracle.model._block in fp64 with every tensor-core operand rounded where the kernels round it):
+    # every tensor, q/k projection gradients included, is held to rtol 2e-2 against the closer of the fp32 oracle and the
+    # yardstick -- what bf16 itself costs (yardstick vs fp32) is printed, not absorbed into a wider bar
+    sdy = {k: v.detach().double().clone().requires_grad_(v.requires_grad) for k, v in sd.items()}
+    xy = x.double().clone().requires_grad_(True)
+    sky = sk.double().clone().requires_grad_(True) if skip else None
+    refy = omodel._block(sdy, "b", xy, cfg, rope, skip=sky, emu=True)
+    refy.backward(go.double())
+    yard = {"out": refy, "dx": xy.grad}
+    if skip:
+        yard["dskip"] = sky.grad
+    for n, p in blk.named_parameters():
+        if p.requires_grad:
+            yard[n] = sdy["b." + n].grad
     for name, a, b in checks:
         l2, mx = rel(a, b)
-        qk = ".q_proj." in name or ".k_proj." in name     # cancellation-dominated (see test_gpu_model.py)
-        assert l2 < (6e-2 if qk else 2e-2) and mx < (1e-1 if qk else 4e-2), f"{name}: rel l2 {l2:.3e}, rel max {mx:.3e}"
+        l2y, mxy = rel(a, yard[name])
+        cost, _ = rel(yard[name], b)
+        print(f"{name}: ours-fp32 {l2:.2e}  ours-yardstick {l2y:.2e}  yardstick-fp32 {cost:.2e}")
+        assert min(l2, l2y) < 2e-2 and min(mx, mxy) < 4e-2, f"{name}: rel l2 {l2:.3e} / {l2y:.3e}, rel max {mx:.3e} / {mxy:.3e}"
 
 
 def test_fused_equals_modular_path():

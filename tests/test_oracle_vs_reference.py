@@ -140,3 +140,101 @@ def test_pointnet_golden_matches_oracle():
                                           st["pointnet_mlp.0.bias"], st["pointnet_mlp.2.weight"], st["pointnet_mlp.2.bias"],
                                           st["fc.0.weight"], st["fc.0.bias"], pooling)
         assert torch.allclose(out, d["out"], rtol=1e-6, atol=1e-7), pooling
+
+
+VARIANTS = {
+    # tag: (strategy, geoembed, mlp_type, scales, use_scale_weights, positional_embedding, num_layers, num_graphs)
+    "multiscale_weighted": (["radius", "radius"], [True, True], "linear", [1.0, 1.5], True, "rope", 2, 1),
+    "multiscale_sum_channel": ("bidirectional", [True, False], "channel", [0.8, 1.3], False, "rope", 3, 1),
+    "absolute_pe": ("knn", [False, False], "linear", [1.0], False, "absolute", 2, 1),
+    "batched": (["radius", "reverse"], [True, False], "linear", [1.0], False, "rope", 2, 2),
+}
+
+
+def _variant_inputs(num_graphs):
+    from tests import synth
+    G = (6, 4, 4)
+    n_per = [700, 500][:num_graphs]
+    pos = torch.cat([torch.from_numpy(synth.surface_cloud(n, seed=21 + i)) for i, n in enumerate(n_per)])
+    c = torch.from_numpy(synth.unit_normals(pos.shape[0], seed=9))
+    bidx = torch.cat([torch.full((n,), i, dtype=torch.long) for i, n in enumerate(n_per)])
+    lat = torch.from_numpy(synth.latent_grid(G))
+    return G, pos, c, bidx, lat
+
+
+@needs_ref
+@pytest.mark.parametrize("tag", list(VARIANTS))
+def test_model_restatement_variants_match_reference(tag):
+    """oracle.model.gaot3d_forward against the reference's own GAOT3D for the option surface the golden models do not
+    reach: multi-scale (+ learned scale weights), mlp_type='channel', absolute PE, a batch of two examples --
+    output and parameter gradients (reference magno.py:502-596, :711-798; gaot_3d.py:102-144, :278-290)."""
+    ref = ref_loader.load_reference()
+    strat, geo, mlp, scales, usw, pe, nl, B = VARIANTS[tag]
+    torch.manual_seed(7)
+    G, pos, c, bidx, lat = _variant_inputs(B)
+    r, k = 0.4, 2
+    MC = ref.magno.MAGNOConfig(gno_coord_dim=3, lifting_channels=16, neighbor_strategy=strat, gno_radius=r, mlp_type=mlp,
+                               precompute_edges=False, use_geoembed=geo, encoder_feature_attr=["pos", "c"], k_neighbors=k,
+                               scales=scales, use_scale_weights=usw)
+    TC = ref.attn.TransformerConfig(patch_size=2, hidden_size=128, num_layers=nl, positional_embedding=pe)
+    TC.attn_config.hidden_size, TC.attn_config.num_heads, TC.attn_config.num_kv_heads = 128, 4, 4
+    TC.ffn_config.hidden_size = 128
+    m = ref.gaot_3d.GAOT3D(6, 4, MC, TC, latent_tokens=G).eval()
+    y = m(ref_loader.SimpleBatch(pos=pos, batch=bidx, num_graphs=B, c=c), tokens_pos=lat)
+    y.pow(2).mean().backward()
+    es, ds = (strat, strat) if isinstance(strat, str) else strat
+    cfg = dict(latent_tokens=G, patch_size=2, lifting_channels=16, radius=r, k=k, enc_strategy=es, dec_strategy=ds,
+               use_geoembed=geo, num_layers=nl, num_heads=4, num_kv_heads=4, norm_eps=1e-6, positional_embedding=pe,
+               scales=scales, use_scale_weights=usw)
+    sd = {n: v.detach().clone().requires_grad_(v.dtype.is_floating_point and "freqs" not in n and n != "latent_tokens")
+          for n, v in m.state_dict().items()}
+    yo = omodel.gaot3d_forward(sd, cfg, pos, [pos, c], latent_pos=lat, keep_graph=True,
+                               batch_idx=bidx if B > 1 else None, num_graphs=B)
+    assert torch.allclose(yo, y, rtol=1e-4, atol=1e-6), tag
+    yo.pow(2).mean().backward()
+    for n, p in m.named_parameters():
+        if p.grad is None:
+            continue
+        assert sd[n].grad is not None, n
+        rel = ((sd[n].grad - p.grad).norm() / p.grad.norm().clamp(min=1e-30)).item()
+        assert rel < 1e-3, (tag, n, rel)
+
+
+@needs_ref
+def test_model_restatement_explicit_edges_match_reference():
+    """Precomputed-edge path (magno.py:506-516, :715-725): int32 edges in arbitrary order handed over on the batch."""
+    ref = ref_loader.load_reference()
+    torch.manual_seed(3)
+    G, pos, c, bidx, lat = _variant_inputs(1)
+    r, k = 0.4, 2
+    MC = ref.magno.MAGNOConfig(gno_coord_dim=3, lifting_channels=16, neighbor_strategy="radius", gno_radius=r, mlp_type="linear",
+                               precompute_edges=True, use_geoembed=[True, False], encoder_feature_attr=["pos", "c"])
+    TC = ref.attn.TransformerConfig(patch_size=2, hidden_size=128, num_layers=2, positional_embedding="rope")
+    TC.attn_config.hidden_size, TC.attn_config.num_heads, TC.attn_config.num_kv_heads = 128, 4, 4
+    TC.ffn_config.hidden_size = 128
+    m = ref.gaot_3d.GAOT3D(6, 4, MC, TC, latent_tokens=G).eval()
+    from oracle import graph as og
+    ee = torch.from_numpy(og.get_neighbor_strategy_np("bidirectional", pos.numpy(), None, lat.numpy(), None, r, k, False))
+    de = torch.from_numpy(og.get_neighbor_strategy_np("radius", pos.numpy(), None, lat.numpy(), None, r, k, True))
+    ee = ee[:, torch.randperm(ee.shape[1])].to(torch.int32)
+    de = de[:, torch.randperm(de.shape[1])].to(torch.int32)
+    y = m(ref_loader.SimpleBatch(pos=pos, c=c, encoder_edge_index_s0=ee, decoder_edge_index_s0=de), tokens_pos=lat)
+    cfg = dict(latent_tokens=G, patch_size=2, lifting_channels=16, radius=r, k=k, enc_strategy="radius", dec_strategy="radius",
+               use_geoembed=[True, False], num_layers=2, num_heads=4, num_kv_heads=4, norm_eps=1e-6, positional_embedding="rope")
+    yo = omodel.gaot3d_forward(m.state_dict(), cfg, pos, [pos, c], latent_pos=lat, enc_edges=[ee], dec_edges=[de])
+    assert torch.allclose(yo, y, rtol=1e-4, atol=1e-6)
+
+
+def test_bf16_yardstick_is_close_to_fp32_oracle():
+    """The bf16-operand yardstick (oracle.model emulate_bf16) is the same function up to operand rounding: its output is
+    within the mixed-precision tier of the fp32 restatement on a golden model."""
+    g = torch.load(os.path.join(GOLD, "model_golden.pt"))["knn"]
+    cfg = dict(latent_tokens=tuple(g["latent_tokens"]), patch_size=2, lifting_channels=32, radius=g["radius"], k=g["k"],
+               enc_strategy="knn", dec_strategy="knn", use_geoembed=g["use_geoembed"], num_layers=3, num_heads=4,
+               num_kv_heads=2, norm_eps=1e-6, positional_embedding="rope")
+    y64 = omodel.gaot3d_forward(g["state"], cfg, g["pos"], [g["pos"], g["c"]], latent_pos=g["tokens_pos"], dtype=torch.float64)
+    assert torch.allclose(y64.float(), g["out"], rtol=1e-4, atol=1e-6)
+    yb = omodel.gaot3d_forward(g["state"], cfg, g["pos"], [g["pos"], g["c"]], latent_pos=g["tokens_pos"], dtype=torch.float64,
+                               emulate_bf16=True)
+    err = (yb - y64).abs().max().item() / y64.abs().max().item()
+    assert 0 < err < 2e-2, err
