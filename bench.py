@@ -1,16 +1,28 @@
 #!/usr/bin/env python
 """bench.py -- GAOT-3D hot path on B200: fwd+bwd samples/s (with GNO edges/s and per-kernel roofline).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload drivaernet500k|small]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME] [--shard | --ddp]
 
-Workload (BASELINE.json configs[1]): DrivAerNet++-shaped 500K-point surface cloud, latent 64x64x32,
-kNN encoder / decoder (k=1), C=32, pos+normals in, 4 output channels (pressure + WSS), 10-layer
-transformer (H=256, 8 heads, FFN 1024, RoPE, patch 2 -> S=16384), one sample per step, fwd + bwd +
-AdamW step, online graph build inside the step.  N>1: one process per GPU, one sample per rank per
-step (the reference's DDP mode), gradients all-reduced over NCCL -> weak scaling.
+N = 1 (BASELINE.json configs[1]): DrivAerNet++-shaped 500K-point surface cloud, latent 64x64x32, kNN encoder / decoder
+(k=1), C=32, pos+normals in, 4 output channels (pressure + WSS), 10-layer transformer (H=256, 8 heads, FFN 1024, RoPE,
+patch 2 -> S=16384), one sample per step, fwd + bwd + AdamW step, online graph build inside the step.  The line also
+carries `extras`: the FP32-GNO tier of the same step, the 8M-point single-GPU step (configs[3] at N=1), config A
+(32K-point forward, CPU reference beside it) and the graph-build sweep (configs[4]) with the CPU search beside it.
+
+N > 1 (BASELINE.json configs[3], the north star's multi-GPU path): ONE DrivaerML-shaped 8M-point sample per step, physical
+points AND latent tokens sharded across the N ranks (gaot_3d_b200/shard.py) -> "scaling": "strong".  The line carries
+`n1_same_workload` (the same 8M step unsharded on rank 0 alone, timed in the same run -- speed-up = n1 ms / ms_per_step),
+`shard_parity` (sharded vs unsharded outputs / gradients on small samples, computed on these NCCL ranks) and `ddp` (the
+reference's own multi-GPU mode: one 500K sample per rank, weak scaling).  `--ddp` makes the DDP run the headline instead.
+
+Timing: W >= 3 warm-up steps, K steps between CUDA events on the launching stream, barrier + synchronize on both sides,
+max over ranks.  The transformer runs as CUDA graphs (tgraph.py), which events cannot look into, so the per-kernel table
+(`kernels`, `roofline`) comes from a SECOND pass of the same K steps with graph replay off and the in-library CUDA events
+on; `value` / `ms_per_step` / `e2e` are from the first.
 Prints ONE JSON line (rank 0).
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -30,12 +42,15 @@ WORKLOADS = {
     "crm500k": dict(n_points=500_000, latent=(64, 64, 32), box="crm", k=1, layers=10, hidden=256, heads=8, ffn=1024,
                     strategy="bidirectional", radius=0.033, geoembed=[True, False], features="mach_aoa"),
     "small": dict(n_points=32_768, latent=(16, 16, 16), box="drivaernet", k=1, layers=4, hidden=256, heads=8, ffn=1024),
-    # BASELINE configs[3]: DrivaerML-shaped full-resolution sample; with --shard the physical points of ONE
-    # sample are split across the ranks (encoder partial sums all-reduced, decoder query-sharded)
+    # BASELINE configs[0]: 32K-point cloud, 16^3 = 4096 latent tokens, radius encoder / reverse decoder (forward timed, CPU beside it)
+    "configA32k": dict(n_points=32_768, latent=(16, 16, 16), box="drivaernet", k=1, layers=10, hidden=256, heads=8, ffn=1024,
+                       strategy=["radius", "reverse"], radius=0.15),
+    # BASELINE configs[3]: DrivaerML-shaped full-resolution sample; sharded, ONE sample is split across the ranks
     "drivaerml8m": dict(n_points=8_000_000, latent=(64, 64, 32), box="drivaerml", k=1, layers=10, hidden=256, heads=8, ffn=1024,
                         strategy=["bidirectional", "reverse"], radius=0.033),
 }
 C_LIFT, C_IN, C_OUT, PATCH = 32, 6, 4, 2
+NODE_MLP = {"fp32": "torch", "tf32": "tf32", "fused": "fused"}
 
 
 def peaks():
@@ -51,15 +66,25 @@ def make_sample(wl, seed):
     pos = synth.surface_cloud(wl["n_points"], wl["box"], seed=seed)
     nrm = synth.mach_aoa(wl["n_points"], seed=seed) if wl.get("features") == "mach_aoa" else synth.unit_normals(wl["n_points"], seed=seed)
     rng = np.random.default_rng(seed + 7)
-    tgt = rng.standard_normal((wl["n_points"], C_OUT)).astype(np.float32)
+    tgt = rng.standard_normal((wl["n_points"], C_OUT), dtype=np.float32)
     return pos, nrm, tgt
 
 
 class ClockSampler:
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
+    """nvidia-smi clocks / throttle reasons every 50 ms; started before the warm-up (the tool needs ~0.5 s to come up), only the
+    samples that arrive between mark_begin() and mark_end() -- the timed region -- are reported."""
+
     def __init__(self, gpu_index):
         self.idx, self.rows, self.proc = str(gpu_index), [], None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def start(self):
         try:
@@ -73,11 +98,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             f = [x.strip() for x in line.split(",")]
             if len(f) >= 8 and f[0] == self.idx:
-                self.rows.append(f)
+                self.rows.append((time.perf_counter(), f))
 
     def stop(self):
         if self.proc is not None:
             self.proc.terminate()
+        inside = [f for t, f in self.rows if self.t0 is None or (self.t0 <= t <= (self.t1 or t) + 0.05)]
+        self.rows = inside if inside else [f for _, f in self.rows[-3:]]        # a region shorter than one sampling period: the latest samples
         sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
         reasons = []
@@ -88,36 +115,57 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def cpu_cfg(wl):
-    return dict(k=wl["k"], C=C_LIFT, hidden=wl["hidden"], heads=wl["heads"], ffn=wl["ffn"], num_layers=wl["layers"], patch=PATCH,
+def cpu_cfg(wl, point_scale=1.0):
+    return dict(strategy=wl.get("strategy", "knn"), radius=wl.get("radius", 0.033), point_scale=point_scale, k=wl["k"], C=C_LIFT, hidden=wl["hidden"], heads=wl["heads"], ffn=wl["ffn"], num_layers=wl["layers"], patch=PATCH,
                 latent_tokens=wl["latent"], enc_mlp=[6, 64, 64, 64, C_LIFT], dec_mlp=[6, 64, 64, C_LIFT])
 
 
-def run_cpu_arm(wl, steps, warmup, name):
-    """The reference's CPU path (oracle port) on the host cores: bounded sample per step."""
+def host_threads():
+    """All host cores, set explicitly: torchrun exports OMP_NUM_THREADS=1, which would pin the CPU arm to one core."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
+def run_cpu_arm(wl, steps, warmup, budget_s=150.0):
+    """The reference's CPU path (oracle port) on the host cores.  One step = one complete fwd+bwd sample (full kNN graph build,
+    full GNO encoder + decoder, ALL transformer blocks).  The number of executed steps is capped so that the run stays inside
+    `budget_s`; the returned `steps` is what actually ran."""
     from oracle import cpu_step
     from tests import synth
     lat = synth.latent_grid(wl["latent"], wl["box"])
-    cores = torch.get_num_threads()
-    times = []
-    for i in range(warmup + steps):
-        pos, nrm, tgt = make_sample(wl, seed=i % 4)
-        r = cpu_step.cpu_step_seconds(pos, nrm, tgt, lat, cpu_cfg(wl), layers_timed=1, search_workers=-1, seed=i)
-        if i >= warmup:
-            times.append(r["seconds"])
-        last = r
+    cores = host_threads()
+    times, last, t_start = [], None, time.perf_counter()
+    done_w = 0
+    # clouds above 1M points: the point-proportional parts (search, GNO encoder / decoder) run on a contiguous 1/ps subsample and are
+    # scaled by ps (flagged `extrapolated`); the transformer does not depend on the point count
+    ps = max(1, wl["n_points"] // 500_000) if wl["n_points"] > 1_000_000 else 1
+    while True:
+        i = done_w + len(times)
+        pos, nrm, tgt = make_sample(dict(wl, n_points=wl["n_points"] // ps), seed=i % 4)
+        # the one-off warm-up step runs 2 blocks only (it exists to page in torch / build the thread pool)
+        r = cpu_step.cpu_step_seconds(pos, nrm, tgt, lat, cpu_cfg(wl, float(ps)), layers_timed=(2 if done_w < warmup else None),
+                                      search_workers=-1, seed=i, single_thread_search=(done_w >= warmup and not times))
+        if done_w < warmup:
+            done_w += 1
+            continue
+        times.append(r["seconds"])
+        last = r if "graph_single_thread" in r["parts"] or last is None else last
+        elapsed = time.perf_counter() - t_start
+        if len(times) >= steps or elapsed + 1.2 * float(np.mean(times)) > budget_s:
+            break
     sec = float(np.mean(times))
-    sample = (f"per step: full kNN graph build (scipy cKDTree, all cores), full GNO encoder+decoder fwd+bwd at E={wl['n_points'] * wl['k']}, "
-              f"1 of {wl['layers']} transformer blocks fwd+bwd at S={(wl['latent'][0] // PATCH) * (wl['latent'][1] // PATCH) * (wl['latent'][2] // PATCH)} "
-              f"scaled x{wl['layers']}; torch CPU fp32, SDPA as in reference attn.py:126")
-    return sec, cores, sample, last["parts"]
+    S = (wl["latent"][0] // PATCH) * (wl["latent"][1] // PATCH) * (wl["latent"][2] // PATCH)
+    sample = (f"per step: full {wl.get('strategy', 'knn')} graph build (scipy cKDTree, all {cores} threads; single-threaded figure in parts_s), full GNO "
+              f"encoder+decoder fwd+bwd" + (f" on a 1/{ps} point subsample scaled x{ps}" if ps > 1 else "") + f" (edges enc/dec {last['parts']['edges_enc_dec']}), all {wl['layers']} transformer blocks fwd+bwd at S={S}; torch CPU fp32, SDPA as in "
+              f"reference attn.py:126; {len(times)} step(s) executed of {steps} requested (capped to ~{budget_s:.0f} s of CPU work)")
+    return sec, cores, sample, last["parts"], len(times), bool(last["extrapolated"])
 
 
 def gno_large_graph(lib, G, pos, lat, dev, pk_hbm, precision, radius=0.033):
     """GNO edges/s where the kernel, not the launch, is what is timed: the radius graphs of the same cloud
     (decoder: every point -> latents within r, ~12 edges per point; encoder: capped at 32 per latent), fused
     GNO forward and backward timed by the in-library CUDA events (outside the step timing)."""
-    import ctypes
     from gaot_3d_b200 import ops
     out = {}
     for name, dec, layers in (("decoder_radius", True, [6, 64, 64, C_LIFT]), ("encoder_radius", False, [6, 64, 64, 64, C_LIFT])):
@@ -152,21 +200,279 @@ def gno_large_graph(lib, G, pos, lat, dev, pk_hbm, precision, radius=0.033):
     return out
 
 
+class Job:
+    """One workload in one parallel mode on this rank.  mode: 'single' (this rank alone, no collectives), 'ddp' (one sample per
+    rank, gradients all-reduced by DistributedDataParallel -- the reference's mode, stat.py:431-436) or 'shard' (ONE sample
+    split across the ranks, shard.py)."""
+
+    def __init__(self, wl_name, mode, dev, rank, world, gno_precision="bf16", node_mlp="fused", nsamp=None):
+        import gaot_3d_b200 as G
+        from tests import synth
+        self.G, self.wl, self.mode, self.dev, self.rank, self.world = G, WORKLOADS[wl_name], mode, dev, rank, world
+        wl = self.wl
+        self.set_tier(gno_precision, node_mlp)
+        torch.manual_seed(0)
+        self.c_in = 5 if wl.get("features") == "mach_aoa" else C_IN
+        mc = G.MAGNOConfig(gno_coord_dim=3, lifting_channels=C_LIFT, neighbor_strategy=wl.get("strategy", "knn"), k_neighbors=wl["k"],
+                           gno_radius=wl.get("radius", 0.033), mlp_type="linear", precompute_edges=False,
+                           use_geoembed=wl.get("geoembed", [False, False]), encoder_feature_attr=["pos", "c"],
+                           in_gno_channel_mlp_hidden_layers=[64, 64, 64], out_gno_channel_mlp_hidden_layers=[64, 64], projection_channels=256)
+        tc = G.TransformerConfig(patch_size=PATCH, hidden_size=wl["hidden"], num_layers=wl["layers"], positional_embedding="rope")
+        tc.attn_config.hidden_size, tc.attn_config.num_heads, tc.attn_config.num_kv_heads = wl["hidden"], wl["heads"], wl["heads"]
+        tc.attn_config.atten_dropout = 0.0
+        tc.ffn_config.hidden_size = wl["ffn"]
+        self.model = G.GAOT3D(self.c_in, C_OUT, mc, tc, latent_tokens=wl["latent"]).to(dev).train()
+        self.model_step = self.model
+        if mode == "ddp" and world > 1:
+            self.model_step = torch.nn.parallel.DistributedDataParallel(self.model, device_ids=[dev.index])
+        self.opt = torch.optim.AdamW(self.model.parameters(), lr=3e-4, weight_decay=1e-5, fused=True)
+        self.lat = torch.from_numpy(synth.latent_grid(wl["latent"], wl["box"])).to(dev)
+        self.n_total = wl["n_points"]
+        self.nsamp = nsamp or (2 if self.n_total > 2_000_000 else 4)
+        self.host = []
+        for s in range(self.nsamp):
+            if mode == "shard" and world > 1:
+                from gaot_3d_b200 import shard as _shard
+                pos, nrm, tgt = make_sample(wl, seed=s)                 # every rank generates the same sample, keeps its range
+                lo, hi = _shard.shard_range(self.n_total, rank, world)
+                pos, nrm, tgt = pos[lo:hi].copy(), nrm[lo:hi].copy(), tgt[lo:hi].copy()
+            else:
+                pos, nrm, tgt = make_sample(wl, seed=s + (100 * rank if mode == "ddp" else 0))
+            self.host.append(tuple(torch.from_numpy(a).pin_memory() for a in (pos, nrm, tgt)))
+        self.resident = [tuple(t.to(dev) for t in h) for h in self.host]
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.host[0])
+        self.samples_per_step = world if mode == "ddp" else 1
+
+    def set_tier(self, gno_precision, node_mlp):
+        self.G.set_gno_precision(gno_precision)
+        self.G.set_node_mlp_mode(NODE_MLP[node_mlp])
+        self.gno_precision, self.node_mlp = gno_precision, node_mlp
+
+    def step(self, sample):
+        pos, nrm, tgt = sample
+        self.opt.zero_grad(set_to_none=True)
+        if self.mode == "shard" and self.world > 1:
+            from gaot_3d_b200 import shard as _shard
+            y = _shard.sharded_forward(self.model, self.G.Batch(pos=pos, c=nrm), self.lat, self.n_total)
+            loss = ((y - tgt) ** 2).sum() / (self.n_total * C_OUT)       # local share of the global mean
+            loss.backward()
+            _shard.allreduce_partial_grads(self.model)
+        else:
+            y = self.model_step(self.G.Batch(pos=pos, c=nrm), tokens_pos=self.lat)
+            loss = torch.nn.functional.mse_loss(y, tgt)
+            loss.backward()
+        self.opt.step()
+        return loss
+
+    def forward_only(self, sample):
+        with torch.no_grad():
+            return self.model(self.G.Batch(pos=sample[0], c=sample[1]), tokens_pos=self.lat)
+
+    def barrier(self):
+        if self.world > 1 and self.mode != "single":
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, n, e2e=False, fn=None):
+        """ms for n steps: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks."""
+        fn = fn or self.step
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        ev0.record()
+        for i in range(n):
+            if e2e:
+                smp = tuple(t.to(self.dev, non_blocking=True) for t in self.host[i % self.nsamp])
+                float(fn(smp).reshape(-1)[0].item())              # D2H read of the step's loss
+            else:
+                fn(self.resident[i % self.nsamp])
+        ev1.record()
+        self.barrier()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=self.dev)
+        if self.world > 1 and self.mode != "single":
+            import torch.distributed as dist
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def warm(self, n):
+        for i in range(n):
+            self.step(self.resident[i % self.nsamp])
+
+    def close(self):
+        from gaot_3d_b200 import tgraph
+        tgraph.reset()
+        self.model = self.model_step = self.opt = self.resident = self.host = None
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+
+
+def kernel_table(lib, job, steps, pk):
+    """Second pass of `steps` steps with graph replay off and the in-library CUDA events on -> per-kernel table."""
+    from gaot_3d_b200 import tgraph
+    tgraph.set_enabled(False)
+    try:
+        job.warm(1)
+        lib.gaot_profile_enable(1)
+        ms_total = job.timed(steps)
+        buf = ctypes.create_string_buffer(1 << 16)
+        lib.gaot_profile_summary(buf, len(buf))
+        lib.gaot_profile_enable(0)
+    finally:
+        tgraph.set_enabled(True)
+    kernels = {}
+    for line in buf.value.decode().strip().splitlines():
+        name, calls, ms, work = line.split()
+        calls, ms, work = int(calls), float(ms), float(work)
+        kernels[name] = {"calls_per_step": calls / steps, "ms_per_step": ms / steps, "share_of_step": ms / ms_total,
+                         "avg_launch_ms": ms / calls, "work_per_launch": work / calls}
+    tensor_bound = {"attn_fwd", "attn_bwd", "linear_fwd", "linear_bwd_x", "linear_bwd_w"}
+    for name, kd in kernels.items():
+        rate = kd["work_per_launch"] / (kd["avg_launch_ms"] * 1e-3)
+        if name in tensor_bound:
+            kd.update(bound="tensor", achieved=rate / 1e12, peak=pk["tf_sust"], unit="TFLOP/s", frac=rate / 1e12 / pk["tf_sust"])
+        else:
+            kd.update(bound="hbm", achieved=rate / 1e9, peak=pk["hbm"], unit="GB/s", frac=rate / 1e9 / pk["hbm"])
+    return kernels, ms_total / steps
+
+
+def cublas_bars(dev, S, hidden, ffn):
+    """cuBLAS (torch.matmul, bf16) beside this library's tcgen05 GEMMs on the step's shapes, same events, same operands."""
+    from gaot_3d_b200 import ops
+    out = {}
+
+    def t(fn, n=30):
+        for _ in range(5):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    for name, (M, N, K) in {"qkv": (S, 3 * hidden, hidden), "o_proj": (S, hidden, hidden), "ffn_w13": (S, 2 * ffn, hidden),
+                            "ffn_w2": (S, hidden, ffn), "skip_proj": (S, hidden, 2 * hidden)}.items():
+        a = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
+        w = torch.randn(N, K, device=dev, dtype=torch.bfloat16)
+        g = torch.randn(M, N, device=dev, dtype=torch.bfloat16)
+        rec = {"M": M, "N": N, "K": K}
+        fl = 2.0 * M * N * K
+        dw = torch.empty(N, K, device=dev, dtype=torch.float32)
+        for kind, ours, lib_fn in (("fwd", lambda: ops._linear_fwd_raw(a, None, w, None, None, torch.bfloat16), lambda: a @ w.t()),
+                                   ("bwd_x", lambda: ops._linear_bwd_x_raw(g, w, torch.bfloat16), lambda: g @ w),
+                                   ("bwd_w", lambda: ops._linear_bwd_w_raw(g, a, dw), lambda: g.t() @ a)):
+            try:
+                to = t(ours)
+            except Exception as e:  # reporting only
+                rec[kind] = {"error": str(e)[:80]}
+                continue
+            tl = t(lib_fn)
+            rec[kind] = {"ours_ms": to, "cublas_ms": tl, "ours_tflops": fl / to / 1e9, "cublas_tflops": fl / tl / 1e9, "ours_over_cublas": tl / to}
+        out[name] = rec
+    return out
+
+
+def graph_sweep(G, dev, cpu=True, sizes=(100_000, 1_000_000, 10_000_000), cpu_budget_s=60.0):
+    """BASELINE configs[4]: online graph build, radius and knn, 100K..10M points against the 64x64x32 latent grid, with the CPU
+    search (oracle.graph on scipy's cKDTree, all host threads) beside it.  The CPU column runs on at most `cpu_q` queries per
+    case and is scaled to the full query count when it had to be cut (flagged)."""
+    from tests import synth
+    from oracle import graph as og
+    lat_np = synth.latent_grid((64, 64, 32), "drivaerml")
+    lat = torch.from_numpy(lat_np).to(dev)
+    out = []
+    t_cpu0 = time.perf_counter()
+    workers = host_threads()
+
+    def gpu_ms(fn, n=5):
+        for _ in range(2):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n, r
+
+    for n in sizes:
+        pos_np = synth.surface_cloud(n, "drivaerml", seed=11)
+        pos = torch.from_numpy(pos_np).to(dev)
+        for strat, dec in (("knn", False), ("radius", False), ("radius", True)):
+            ms, ei = gpu_ms(lambda: G.get_neighbor_strategy(strat, pos, None, lat, None, 0.033, 1, dec))
+            rec = {"n_points": n, "strategy": strat, "side": "decoder" if dec else "encoder", "edges": int(ei.shape[1]), "gpu_ms": ms,
+                   "gpu_points_per_s": n / (ms * 1e-3)}
+            if cpu and time.perf_counter() - t_cpu0 < cpu_budget_s:
+                # queries: knn -> every phys point looks up its latent; radius enc -> every latent scans phys; radius dec -> every phys scans latents
+                cut = 1_000_000
+                t0 = time.perf_counter()
+                if strat == "knn":
+                    q = pos_np[:cut]
+                    og.knn_np(lat_np, q, 1, workers=workers)
+                    frac = len(q) / n
+                elif not dec:
+                    og.radius_np(pos_np, lat_np, 0.033, workers=workers)
+                    frac = 1.0
+                else:
+                    q = pos_np[:cut]
+                    og.radius_np(lat_np, q, 0.033, workers=workers)
+                    frac = len(q) / n
+                sec = (time.perf_counter() - t0) / frac
+                rec.update(cpu_ms=sec * 1e3, cpu_threads=workers, cpu_scaled_from_fraction=frac, speedup=sec * 1e3 / ms)
+            out.append(rec)
+        del pos
+    return out
+
+
+def config_a(dev, rank, world):
+    """BASELINE configs[0]: forward on a 32K-point cloud, 4096 latent tokens, radius encoder / reverse decoder; the reference's
+    CPU path (oracle.model restatement, torch CPU fp32) timed beside it on the same inputs, and compared."""
+    from oracle import model as omodel
+    job = Job("configA32k", "single", dev, rank, world, nsamp=2)
+    wl = job.wl
+    job.model.eval()
+    for _ in range(3):
+        job.forward_only(job.resident[0])
+    ms = job.timed(10, fn=job.forward_only) / 10
+    y = job.forward_only(job.resident[0]).float().cpu()
+    cfg = dict(latent_tokens=wl["latent"], patch_size=PATCH, lifting_channels=C_LIFT, radius=wl["radius"], k=wl["k"], enc_strategy="radius",
+               dec_strategy="reverse", use_geoembed=[False, False], num_layers=wl["layers"], num_heads=wl["heads"], num_kv_heads=wl["heads"],
+               norm_eps=1e-6, positional_embedding="rope")
+    sd = {k: v.detach().cpu() for k, v in job.model.state_dict().items()}
+    pos, nrm = job.host[0][0], job.host[0][1]
+    cores = host_threads()
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        yo = omodel.gaot3d_forward(sd, cfg, pos, [pos, nrm], latent_pos=job.lat.cpu())
+        cpu_s = time.perf_counter() - t0
+    err = (y - yo).abs().max().item() / yo.abs().max().item()
+    job.close()
+    return {"workload": "32768-point cloud, latent 16x16x16, radius(0.15) encoder / reverse decoder, 10-layer transformer S=512, forward only",
+            "gpu_forward_ms": ms, "gpu_samples_per_s": 1e3 / ms, "cpu_forward_ms": cpu_s * 1e3, "cpu_cores": cores, "cpu_kind": "port (oracle.model)",
+            "max_abs_err_over_max_ref": err}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="drivaernet500k", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra keys (FP32 tier, 8M single-GPU step, config A, graph sweep, cuBLAS bars, DDP)")
     ap.add_argument("--gno-precision", default="bf16", choices=["fp32", "bf16"],
                     help="per-edge kernel MLP operands: bf16 tcgen05 (rtol 2e-2 tier of the north star, default) or fp32 CUDA cores (rtol 1e-5 tier)")
     ap.add_argument("--node-mlp", default="fused", choices=["fp32", "tf32", "fused"],
                     help="node-level MLPs (lifting / projection / recovery): strict fp32 torch GEMMs, TF32 torch GEMMs (what the reference's "
                          "default Conv1d node MLPs get from cuDNN), or TF32 + the fused f16/bf16 tensor-core kernel for the projection head")
-    ap.add_argument("--shard", action="store_true", help="intra-sample sharding: all ranks cooperate on ONE sample (strong scaling)")
+    ap.add_argument("--shard", action="store_true", help="intra-sample sharding: all ranks cooperate on ONE sample (strong scaling; default for N > 1)")
+    ap.add_argument("--ddp", action="store_true", help="N > 1: one sample per rank (the reference's DDP mode, weak scaling) as the headline")
+    ap.add_argument("--shard-mode", default="sp", choices=["sp", "hp"], help="sharded transformer: token-sharded (sp) or round 1's replicated + head-parallel (hp)")
     ap.add_argument("--profile-step", action="store_true", help="warm up, then run ONE step between cudaProfilerStart/Stop (for ncu --profile-from-start off) and exit")
+    ap.add_argument("--no-graph", action="store_true", help="issue the transformer's kernels one by one instead of replaying its CUDA graphs")
     args = ap.parse_args()
     # the contract is ONE JSON line on stdout: libraries that print to the C-level stdout (NCCL prints its version line
     # there) are sent to stderr; the JSON line goes to the saved descriptor
@@ -176,10 +482,14 @@ def main():
     def emit(obj):
         os.write(real_stdout, (json.dumps(obj) + "\n").encode())
 
-    wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not args.ddp:
+        args.shard = True
+    mode = "single" if world == 1 else ("shard" if args.shard else "ddp")
+    wl_name = args.workload or ("drivaerml8m" if mode == "shard" else "drivaernet500k")
+    wl = WORKLOADS[wl_name]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     S = (wl["latent"][0] // PATCH) * (wl["latent"][1] // PATCH) * (wl["latent"][2] // PATCH)
     strat = wl.get("strategy", "knn")
@@ -190,30 +500,29 @@ def main():
     config = {"workload": f"{shape}-shaped {wl['n_points']}-point surface cloud, latent {wl['latent']}, {strat_txt}, "
                           f"C={C_LIFT}, in {c_in} ({'pos+Mach/AOA' if c_in == 5 else 'pos+normals'}), out 4 (pressure+WSS), "
                           f"geoembed {wl.get('geoembed', [False, False])}, {wl['layers']}-layer transformer H={wl['hidden']} S={S}, "
-                          f"fwd+bwd+AdamW, online graph build, batch 1/GPU, atten_dropout 0",
+                          f"fwd+bwd+AdamW, online graph build, " + ("ONE sample per step split across the ranks" if mode == "shard" else "batch 1/GPU") +
+                          ", atten_dropout 0",
               "n_points": wl["n_points"], "latent_tokens": list(wl["latent"]), "seq_len": S,
-              "parallelism": (f"shard{world} (one sample split across ranks)" if args.shard else f"dp{world}") if world > 1 else "single",
-              "l2": "per-step working set (>1 GB of activations) exceeds the 126 MB L2; 4 distinct samples cycled"}
+              "parallelism": {"single": "single", "ddp": f"dp{world}", "shard": f"shard{world} ({args.shard_mode}: physical points + latent tokens split across ranks)"}[mode],
+              "l2": "per-step working set (>1 GB of activations) exceeds the 126 MB L2; distinct samples cycled"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
             return
-        sec, cores, sample, parts = run_cpu_arm(wl, args.steps, min(args.warmup, 1), "reference")
+        sec, cores, sample, parts, ran, extrap = run_cpu_arm(wl, args.steps, min(args.warmup, 1))
         v = 1.0 / sec
         emit({"impl": "reference", "metric": "fwd+bwd samples/s", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
-                          "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
-                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                          "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample,
-                                           "parts_s": parts},
-                          "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+              "steps": ran, "steps_requested": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
+              "scaling": "strong" if mode == "shard" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+              "extrapolated": extrap,
+              "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample, "parts_s": parts},
+              "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
 
     # ------------------------------------------------------------------ our arm (B200)
     import gaot_3d_b200 as G
-    from gaot_3d_b200 import _lib, ops
-    from tests import synth
-    import ctypes
+    from gaot_3d_b200 import _lib, tgraph
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback)")
     dev = torch.device("cuda", local_rank)
@@ -222,117 +531,36 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
-    G.set_gno_precision(args.gno_precision)
-    G.set_node_mlp_mode({"fp32": "torch", "tf32": "tf32", "fused": "fused"}[args.node_mlp])
-    torch.manual_seed(0)
-    mc = G.MAGNOConfig(gno_coord_dim=3, lifting_channels=C_LIFT, neighbor_strategy=wl.get("strategy", "knn"), k_neighbors=wl["k"],
-                       gno_radius=wl.get("radius", 0.033),
-                       mlp_type="linear", precompute_edges=False, use_geoembed=wl.get("geoembed", [False, False]), encoder_feature_attr=["pos", "c"],
-                       in_gno_channel_mlp_hidden_layers=[64, 64, 64], out_gno_channel_mlp_hidden_layers=[64, 64], projection_channels=256)
-    tc = G.TransformerConfig(patch_size=PATCH, hidden_size=wl["hidden"], num_layers=wl["layers"], positional_embedding="rope")
-    tc.attn_config.hidden_size, tc.attn_config.num_heads, tc.attn_config.num_kv_heads = wl["hidden"], wl["heads"], wl["heads"]
-    tc.attn_config.atten_dropout = 0.0
-    tc.ffn_config.hidden_size = wl["ffn"]
-    model = G.GAOT3D(c_in, C_OUT, mc, tc, latent_tokens=wl["latent"]).to(dev).train()
-    if world > 1 and not args.shard:
-        model_step = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank])
-    else:
-        model_step = model
-    opt = torch.optim.AdamW(model.parameters(), lr=3e-4, weight_decay=1e-5, fused=True)
-    lat = torch.from_numpy(synth.latent_grid(wl["latent"], wl["box"])).to(dev)
-    host = []
-    n_total = wl["n_points"]
-    nsamp = 2 if n_total > 2_000_000 else 4
-    for s in range(nsamp):
-        if args.shard and world > 1:
-            from gaot_3d_b200 import shard as _shard
-            pos, nrm, tgt = make_sample(wl, seed=s)                 # every rank generates the same sample, keeps its range
-            lo, hi = _shard.shard_range(n_total, rank, world)
-            pos, nrm, tgt = pos[lo:hi].copy(), nrm[lo:hi].copy(), tgt[lo:hi].copy()
-        else:
-            pos, nrm, tgt = make_sample(wl, seed=s + 100 * rank)
-        host.append(tuple(torch.from_numpy(a).pin_memory() for a in (pos, nrm, tgt)))
-    resident = [tuple(t.to(dev) for t in h) for h in host]
-    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
-
-    def step(sample):
-        pos, nrm, tgt = sample
-        opt.zero_grad(set_to_none=True)
-        if args.shard and world > 1:
-            y = _shard.sharded_forward(model, G.Batch(pos=pos, c=nrm), lat, n_total)
-            loss = ((y - tgt) ** 2).sum() / (n_total * C_OUT)       # local share of the global mean
-            loss.backward()
-            _shard.allreduce_partial_grads(model)
-        else:
-            y = model_step(G.Batch(pos=pos, c=nrm), tokens_pos=lat)
-            loss = torch.nn.functional.mse_loss(y, tgt)
-            loss.backward()
-        opt.step()
-        return loss
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(n, e2e):
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        ev0.record()
-        for i in range(n):
-            if e2e:
-                smp = tuple(t.to(dev, non_blocking=True) for t in host[i % nsamp])
-                float(step(smp).item())                     # D2H read of the step's loss
-            else:
-                step(resident[i % nsamp])
-        ev1.record()
-        barrier()
-        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
-
-    for i in range(args.warmup):
-        step(resident[i % nsamp])
+    if args.no_graph:
+        tgraph.set_enabled(False)
+    if mode == "shard":
+        from gaot_3d_b200 import shard as _shard
+        _shard.set_default_mode(args.shard_mode)
+    clocks = ClockSampler(local_rank)
+    if not args.profile_step:
+        clocks.start()
+    job = Job(wl_name, mode, dev, rank, world, args.gno_precision, args.node_mlp)
+    job.warm(args.warmup)
     if args.profile_step:
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
-        step(resident[0])
+        job.step(job.resident[0])
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    lib.gaot_profile_enable(1)
     lib.gaot_launch_count_reset()
-    ms_total = timed(args.steps, e2e=False)
+    clocks.mark_begin()
+    ms_total = job.timed(args.steps)
+    clocks.mark_end()
     launches = int(lib.gaot_launch_count())
-    buf = ctypes.create_string_buffer(1 << 16)
-    lib.gaot_profile_summary(buf, len(buf))
-    lib.gaot_profile_enable(0)
     clk = clocks.stop()
-    ms_e2e = timed(args.steps, e2e=True)
-    gno_large = gno_large_graph(lib, G, resident[0][0], lat, dev, pk_hbm=peaks()["hbm"], precision=args.gno_precision) \
-        if (world == 1 and wl["n_points"] <= 1_000_000) else None
+    ms_e2e = job.timed(args.steps, e2e=True)
+    pk = peaks()
+    kernels, ms_eager = kernel_table(lib, job, args.steps, pk)
 
     ms_step = ms_total / args.steps
-    samples_per_step = 1 if (args.shard and world > 1) else world
-    value = samples_per_step * args.steps / (ms_total * 1e-3)
-    e2e_value = samples_per_step * args.steps / (ms_e2e * 1e-3)
-    pk = peaks()
-    kernels = {}
-    for line in buf.value.decode().strip().splitlines():
-        name, calls, ms, work = line.split()
-        calls, ms, work = int(calls), float(ms), float(work)
-        kernels[name] = {"calls_per_step": calls / args.steps, "ms_per_step": ms / args.steps, "share_of_step": ms / ms_total,
-                         "avg_launch_ms": ms / calls, "work_per_launch": work / calls}
-    tensor_bound = {"attn_fwd", "attn_bwd", "linear_fwd", "linear_bwd_x", "linear_bwd_w"}
-    for name, kd in kernels.items():
-        rate = kd["work_per_launch"] / (kd["avg_launch_ms"] * 1e-3)
-        if name in tensor_bound:
-            kd.update(bound="tensor", achieved=rate / 1e12, peak=pk["tf_sust"], unit="TFLOP/s", frac=rate / 1e12 / pk["tf_sust"])
-        else:
-            kd.update(bound="hbm", achieved=rate / 1e9, peak=pk["hbm"], unit="GB/s", frac=rate / 1e9 / pk["hbm"])
+    value = job.samples_per_step * args.steps / (ms_total * 1e-3)
+    e2e_value = job.samples_per_step * args.steps / (ms_e2e * 1e-3)
     dom = max(kernels, key=lambda n: kernels[n]["ms_per_step"]) if kernels else None
     roofline = None
     if dom:
@@ -345,7 +573,9 @@ def main():
             traffic = json.load(open(tpath)).get(dom)
         roofline = {"kernel": dom, "bound": kd["bound"], "achieved": kd["achieved"], "peak": kd["peak"], "unit": kd["unit"],
                     "frac": kd["frac"], "traffic": traffic, "peak_source": f"{pk['src']} (MEASURED_PEAKS.json, sustained bf16 / copy bandwidth)",
-                    "share_of_step": kd["share_of_step"]}
+                    "share_of_step": kd["ms_per_step"] / ms_step,
+                    "timing": "CUDA events around each launch on the launching stream, second pass of the same steps with CUDA-graph replay off "
+                              f"({ms_eager:.2f} ms/step eager vs {ms_step:.2f} replayed)"}
     E = wl["n_points"] * wl["k"]
     gno = {}
     if "gno_fwd" in kernels and "gno_bwd" in kernels and wl.get("strategy", "knn") == "knn":     # E is known only for the knn graphs
@@ -354,21 +584,79 @@ def main():
                "fwd_bwd_edges_per_s": E / ((f["avg_launch_ms"] + b["avg_launch_ms"]) * 1e-3),
                "note": "encoder and decoder launches averaged (same E for knn k=1)", "precision": args.gno_precision}
     out = {"metric": "fwd+bwd samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if args.shard else "weak", "vs_baseline": None,
+           "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if mode == "shard" else "weak", "vs_baseline": None,
            "dtype": ("bf16 tensor-core operands / f32 accumulate (attention, transformer dense layers" +
                      (", GNO edge MLP)" if args.gno_precision == "bf16" else "); f32 GNO edge MLP") +
-                     f"; f32 residual stream, statistics, optimizer; node MLPs {args.node_mlp}"), "data": "synthetic",
-           "config": config, "clocks": clk,
-           "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                     f"; f32 residual stream, statistics, optimizer; node MLPs {args.node_mlp}"),
+           "precision_tier": "bf16 (north star rtol 2e-2 tier)" if args.gno_precision == "bf16" else "fp32 GNO / bf16 transformer",
+           "data": "synthetic", "config": config, "clocks": clk,
+           "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": job.h2d_bytes, "d2h_bytes_per_step": 4,
                    "ms_per_step": ms_e2e / args.steps},
-           "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "gno_edges_per_s": gno}
-    if gno_large:
-        out["gno_edges_per_s"]["large_graphs"] = gno_large
+           "gpu_launches": launches, "cuda_graphs": bool(tgraph.enabled()), "roofline": roofline, "kernels": kernels, "gno_edges_per_s": gno}
+
+    extras = {}
+    if not args.no_extras:
+        if world == 1:
+            if wl["n_points"] <= 1_000_000:
+                out["gno_edges_per_s"]["large_graphs"] = gno_large_graph(lib, G, job.resident[0][0], job.lat, dev, pk_hbm=pk["hbm"],
+                                                                         precision=args.gno_precision)
+            if args.gno_precision == "bf16":                                  # FP32-GNO tier of the same step (strict fp32 node MLPs)
+                job.set_tier("fp32", "fp32")
+                job.warm(2)
+                ms32 = job.timed(max(3, args.steps // 2)) / max(3, args.steps // 2)
+                extras["fp32_gno_tier"] = {"ms_per_step": ms32, "value": 1e3 / ms32, "unit": "samples/s",
+                                           "note": "GNO edge MLP + node MLPs in strict fp32 (rtol 1e-5 tier); transformer bf16 operands in both tiers"}
+                job.set_tier(args.gno_precision, args.node_mlp)
+            extras["cublas_bars"] = cublas_bars(dev, S, wl["hidden"], wl["ffn"])
+            job.close()
+            try:
+                extras["config_a_32k"] = config_a(dev, rank, world)
+            except Exception as e:  # reporting only
+                extras["config_a_32k"] = {"error": repr(e)[:200]}
+            if wl_name == "drivaernet500k":
+                try:
+                    j8 = Job("drivaerml8m", "single", dev, rank, world, args.gno_precision, args.node_mlp)
+                    j8.warm(3)
+                    n8 = max(3, args.steps // 3)
+                    ms8 = j8.timed(n8) / n8
+                    extras["drivaerml8m_single_gpu"] = {"ms_per_step": ms8, "value": 1e3 / ms8, "unit": "samples/s", "steps": n8,
+                                                        "workload": "DrivaerML-shaped 8M-point sample, bidirectional encoder / reverse decoder, fwd+bwd+AdamW"}
+                    j8.close()
+                except Exception as e:
+                    extras["drivaerml8m_single_gpu"] = {"error": repr(e)[:200]}
+            try:
+                extras["graph_sweep"] = graph_sweep(G, dev, cpu=not args.no_cpu_baseline)
+            except Exception as e:
+                extras["graph_sweep"] = {"error": repr(e)[:200]}
+        elif mode == "shard":
+            from tests import shard_worker
+            job.close()
+            extras["shard_parity"] = shard_worker.parity_cases(dev, rank, world, mode=args.shard_mode, verbose=False)
+            # the same workload unsharded on rank 0 alone, same run (the N = 1 point of the strong-scaling curve)
+            n1 = None
+            if rank == 0:
+                j1 = Job(wl_name, "single", dev, rank, world, args.gno_precision, args.node_mlp)
+                j1.warm(3)
+                k1 = max(3, args.steps // 2)
+                ms1 = j1.timed(k1) / k1
+                n1 = {"ms_per_step": ms1, "value": 1e3 / ms1, "unit": "samples/s", "steps": k1, "note": "rank 0 alone, unsharded, other ranks idle"}
+                j1.close()
+            dist.barrier()
+            extras["n1_same_workload"] = n1
+            jd = Job("drivaernet500k", "ddp", dev, rank, world, args.gno_precision, args.node_mlp)
+            jd.warm(3)
+            msd = jd.timed(args.steps)
+            extras["ddp"] = {"value": world * args.steps / (msd * 1e-3), "unit": "samples/s", "ms_per_step": msd / args.steps, "scaling": "weak",
+                             "workload": "DrivAerNet++-shaped 500K-point sample per rank (the reference's DistributedDataParallel mode, stat.py:431-436)"}
+            jd.close()
+    if extras:
+        out["extras"] = extras
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             try:
-                sec, cores, sample, parts = run_cpu_arm(wl, 1, 1, "cpu_baseline")
-                out["cpu_baseline"] = {"value": 1.0 / sec, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample, "parts_s": parts}
+                sec, cores, sample, parts, ran, extrap = run_cpu_arm(wl, 1, 1, budget_s=60.0)
+                out["cpu_baseline"] = {"value": 1.0 / sec, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample, "parts_s": parts,
+                                       "extrapolated": extrap}
             except Exception as e:  # the baseline is reporting only; never lose the GPU line
                 out["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port", "sample": f"failed: {e}"}
         emit(out)

@@ -25,6 +25,7 @@ _SIGS = {
     "gaot_abi_version": (c_int, []),
     "gaot_launch_count": (c_int64, []),
     "gaot_launch_count_reset": (None, []),
+    "gaot_launch_count_add": (None, [c_int64]),
     "gaot_profile_enable": (None, [c_int]),
     "gaot_profile_summary": (c_int, [c_char_p, c_size_t]),
     "gaot_radius_workspace_bytes": (c_size_t, [c_int64, c_int64]),

@@ -44,6 +44,7 @@ const char* gaot_last_error(void) { return g_err; }
 int gaot_abi_version(void) { return 1; }
 int64_t gaot_launch_count(void) { return g_launches.load(); }
 void gaot_launch_count_reset(void) { g_launches.store(0); }
+void gaot_launch_count_add(int64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void gaot_profile_enable(int on) {
     g_prof_on.store(on ? 1 : 0);

@@ -63,23 +63,34 @@ class GAOT3D(nn.Module):
         pe[:, 1::2] = torch.cos(ang).sum(dim=1)
         return pe
 
-    def process(self, rndata: Optional[torch.Tensor] = None, condition: Optional[float] = None) -> torch.Tensor:
+    def process(self, rndata: Optional[torch.Tensor] = None, condition: Optional[float] = None, slab=(0, 1)) -> torch.Tensor:
+        """rndata [B, n, C] -> [B, n, C] (reference gaot_3d.py:166-222).  `slab = (r, R)` (extension, shard.py): `rndata`
+        holds only the r-th of R equal D-slabs of the latent grid (a contiguous token range, and a contiguous patch
+        range: both orders are D-major); the blocks then run in tblock's sequence-parallel mode."""
+        from . import tgraph
         B, n, C = rndata.shape
+        r, R = slab
         D, H, W, P = self.D, self.H, self.W, self.patch_size
-        assert n == D * H * W, f"n_regional_nodes ({n}) is not equal to D*H*W ({D * H * W})"
+        assert n * R == D * H * W, f"n_regional_nodes ({n * R}) is not equal to D*H*W ({D * H * W})"
         assert D % P == 0 and H % P == 0 and W % P == 0, "Dimensions must be divisible by patch size"
-        nd, nh, nw = D // P, H // P, W // P
+        assert (D // P) % R == 0, "latent slabs must hold whole patch planes"
+        if condition is None:                       # the whole processor as two CUDA graphs (tgraph.py) when it fits
+            y = tgraph.process(self, rndata, slab)
+            if y is not None:
+                return y
+        nd, nh, nw = D // P // R, H // P, W // P
         x = rndata.view(B, nd, P, nh, P, nw, P, C).permute(0, 1, 3, 5, 2, 4, 6, 7).contiguous()
         x = _lin(self.patch_linear, x.view(B, nd * nh * nw, P * P * P * C))
+        S_l = nd * nh * nw
         pos = self.positions.to(x.device)
         relative_positions = None
         if self.positional_embedding_name == "absolute":
-            x = x + self._compute_absolute_embeddings(pos, P * P * P * self.node_latent_size)
+            x = x + self._compute_absolute_embeddings(pos, P * P * P * self.node_latent_size)[r * S_l:(r + 1) * S_l]
         elif self.positional_embedding_name == "rope":
             relative_positions = pos        # only a flag: RoPE is 1-D over the flattened patch index
         x = self.processor(x, condition=condition, relative_positions=relative_positions)
         x = x.view(B, nd, nh, nw, P, P, P, C).permute(0, 1, 4, 2, 5, 3, 6, 7).contiguous()
-        return x.view(B, D * H * W, C)
+        return x.view(B, n, C)
 
     def forward(self, batch, tokens_pos: Optional[torch.Tensor] = None, tokens_batch_idx: Optional[torch.Tensor] = None,
                 query_coord_pos: Optional[torch.Tensor] = None, query_coord_batch_idx: Optional[torch.Tensor] = None,

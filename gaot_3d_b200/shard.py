@@ -1,15 +1,21 @@
 """Intra-sample sharding of one large mesh across the GPUs of a node (new -- the
 reference only has sample-level DDP, src/trainer/stat.py:431-436).
 
-Partitioning: rank r owns the contiguous physical-point index range [r*N/R, (r+1)*N/R); latent tokens,
-all weights and the transformer are replicated.
-  encoder : local edges (local phys shard x all latents) -> GNO partial SUMS [M,C] + counts [M]
-            -> NCCL all-reduce(SUM) -> mean.   The radius cap (first 32 per latent by ascending phys
-            index, globally) is restored with one all-gather of per-latent counts: contiguous index
+Partitioning: rank r owns the contiguous physical-point index range [r*N/R, (r+1)*N/R) AND the r-th D-slab of the
+latent grid (a contiguous token range [r*M/R, (r+1)*M/R) = a contiguous patch range); weights are replicated, no
+activation is.
+  encoder : local edges (local phys shard x all latents) -> GNO partial SUMS [M,C] with the edge COUNT as one more
+            column -> ONE reduce-scatter(SUM) -> mean on the local token slab.   The radius cap (first 32 per latent by
+            ascending phys index, globally) is restored with one all-gather of per-latent counts: contiguous index
             ranges make "ascending index" compose as an exclusive prefix over ranks.
-  decoder : queries (phys) sharded, sources (latents) replicated -> no forward communication.
-  backward: d latent from the local decoder is a partial sum -> all-reduce before the replicated
-            transformer backward; GNO-side parameter grads are partial -> all-reduce (allreduce_partial_grads).
+  processor: sequence-parallel (tblock "sp" mode): every GEMM / norm on the S/R local tokens, two all-to-alls per block
+            and direction around the head-sharded attention core, recorded into the processor's CUDA graphs (tgraph.py).
+  decoder : all-gather of the processed latent slabs -> queries (phys) sharded, sources (latents) complete -> no further
+            forward communication.
+  backward: the all-gather's backward is a reduce-scatter of the partial d latent, the reduce-scatter's an all-gather;
+            every parameter gradient is a partial sum (over local points or local tokens) -> one flat all-reduce
+            (allreduce_partial_grads).
+`mode="hp"` keeps round 1's layout (replicated transformer, attention core split by heads) for comparison.
 One process per GPU; collectives go through torch.distributed (NCCL over NVLink/NVSwitch on the box,
 gloo in the CPU tests).
 """
@@ -59,6 +65,76 @@ class _AllReduceBwd(torch.autograd.Function):
         g = g.contiguous().clone()
         dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
         return g, None
+
+
+class _ReduceScatterFwd(torch.autograd.Function):
+    """y_r = (sum over ranks of x)[slab r]  (x [M, W] partial sums, y [M/R, W]).  Backward: all-gather of the slab
+    gradients -- every rank's partial sums fed every slab."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        R = dist.get_world_size(group)
+        x = x.contiguous()
+        y = torch.empty((x.shape[0] // R,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        _reduce_scatter(y, x, group)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        R = dist.get_world_size(ctx.group)
+        g = g.contiguous()
+        out = torch.empty((g.shape[0] * R,) + tuple(g.shape[1:]), dtype=g.dtype, device=g.device)
+        _all_gather(out, g, ctx.group)
+        return out, None
+
+
+class _AllGatherFwd(torch.autograd.Function):
+    """y = concat over ranks of x_r (row slabs).  Backward: reduce-scatter(SUM) of the per-rank partial gradients."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        R = dist.get_world_size(group)
+        x = x.contiguous()
+        out = torch.empty((x.shape[0] * R,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        _all_gather(out, x, group)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        R = dist.get_world_size(ctx.group)
+        g = g.contiguous()
+        y = torch.empty((g.shape[0] // R,) + tuple(g.shape[1:]), dtype=g.dtype, device=g.device)
+        _reduce_scatter(y, g, ctx.group)
+        return y, None
+
+
+def _reduce_scatter(out, inp, group):
+    if inp.is_cuda:
+        dist.reduce_scatter_tensor(out, inp, op=dist.ReduceOp.SUM, group=group)
+    else:       # gloo (CPU tests) has no reduce_scatter: all-reduce a copy and keep the own slab
+        tmp = inp.clone()
+        dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=group)
+        n = out.shape[0]
+        out.copy_(tmp[dist.get_rank(group) * n:(dist.get_rank(group) + 1) * n])
+
+
+def _all_gather(out, inp, group):
+    if inp.is_cuda:
+        dist.all_gather_into_tensor(out, inp, group=group)
+    else:
+        parts = [torch.empty_like(inp) for _ in range(dist.get_world_size(group))]
+        dist.all_gather(parts, inp, group=group)
+        out.copy_(torch.cat(parts, dim=0))
+
+
+def reduce_scatter_forward(x, group=None):
+    return _ReduceScatterFwd.apply(x, group)
+
+
+def all_gather_forward(x, group=None):
+    return _AllGatherFwd.apply(x, group)
 
 
 def all_reduce_forward(x, group=None):
@@ -129,10 +205,23 @@ def global_zscore(feat_local: torch.Tensor, n_total: int, group=None) -> torch.T
     return (feat_local - mean.float()) / std
 
 
+_DEFAULT = {"mode": "sp"}
+
+
+def set_default_mode(mode: str) -> None:
+    """Process-wide default of `sharded_forward(mode=None)` / `allreduce_partial_grads(mode=None)`: "sp" or "hp"."""
+    if mode not in ("sp", "hp"):
+        raise ValueError("shard mode must be 'sp' or 'hp'")
+    _DEFAULT["mode"] = mode
+
+
 def sharded_forward(model, batch_local, tokens_pos, n_total: int, group=None, enc_edges: Optional[torch.Tensor] = None,
-                    head_parallel: bool = True):
+                    head_parallel: bool = True, mode: Optional[str] = None):
     """GAOT3D forward on this rank's shard of ONE sample (batch of one).  Returns the local rows of
-    the output [N_local, C_out].  `model` is a gaot_3d_b200.GAOT3D (single scale, use_gno=True)."""
+    the output [N_local, C_out].  `model` is a gaot_3d_b200.GAOT3D (single scale, use_gno=True).
+    mode "sp": token-sharded processor (nothing replicated); "hp": round 1's replicated processor with a head-parallel
+    attention core (`head_parallel=False`: fully replicated)."""
+    mode = mode or _DEFAULT["mode"]
     enc, dec = model.encoder, model.decoder
     if len(enc.scales) != 1 or not enc.use_gno:
         raise NotImplementedError("sharded path: single scale with the GNO enabled")
@@ -147,31 +236,37 @@ def sharded_forward(model, batch_local, tokens_pos, n_total: int, group=None, en
         if side.use_geoembed and side.geoembed.method != "statistical":
             raise NotImplementedError("sharded path: geometric embedding method must be 'statistical'")
     from .layers.magno import _apply_node_mlp
+    from . import tblock
     dev = batch_local.pos.device
     lat = tokens_pos.to(dev)
     M = lat.shape[0]
     pos = batch_local.pos
+    R, rank = dist.get_world_size(group), dist.get_rank(group)
+    heads = model.processor.encoder_layers[0].attn if len(model.processor.encoder_layers) else model.processor.middle_layer.attn
+    sp = mode == "sp" and R > 1
+    if sp and ((model.D // model.patch_size) % R or heads.num_heads % R or heads.num_kv_heads % R):
+        raise NotImplementedError("sequence-parallel processor: patch planes and head counts must be divisible by the ranks")
     if enc_edges is None:
         enc_edges = local_encoder_edges(enc.encoder_strategy, pos, lat, enc.gno_radius, enc.k_neighbors, group)
     lifted = _apply_node_mlp(enc.lifting, enc.mlp_type, enc._features(batch_local))
     part = enc.gno(y_pos=pos, x_pos=lat, edge_index=enc_edges, f_y=lifted, reduce="sum")       # partial sums [M,C]
     cnt = torch.bincount(enc_edges[1], minlength=M).to(part.dtype)
-    dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
-    latent = all_reduce_forward(part, group) / cnt.clamp(min=1).unsqueeze(1)
+    fused = torch.cat([part, cnt.unsqueeze(1)], dim=1)                # sums and counts travel in ONE collective
+    lo, hi = (rank * (M // R), (rank + 1) * (M // R)) if sp else (0, M)
+    tot = reduce_scatter_forward(fused, group) if sp else all_reduce_forward(fused, group)
+    latent = tot[:, :-1] / tot[:, -1:].detach().clamp(min=1)
     if enc.use_geoembed:
         # the neighbours of a latent token are spread over the ranks: all-reduce the moment SUMS, then every rank
         # finishes (eigenvalues, z-score over all tokens) identically; coordinates carry no gradient
-        geo = enc.geoembed.mlp(sharded_encoder_geo_features(pos, lat, enc_edges, group))
-        latent = _apply_node_mlp(enc.recovery, enc.mlp_type, torch.cat([latent, geo], dim=-1))
-    # the transformer is replicated; its attention core splits by heads across the ranks when the head counts divide
-    # (tblock.set_head_parallel: all-gather of the head outputs forward, of dqkv backward; same kernels, same numbers)
-    from . import tblock
-    tblock.set_head_parallel(head_parallel, group)
+        feats = sharded_encoder_geo_features(pos, lat, enc_edges, group)[lo:hi]
+        latent = _apply_node_mlp(enc.recovery, enc.mlp_type, torch.cat([latent, enc.geoembed.mlp(feats)], dim=-1))
+    tblock.set_head_parallel(sp or head_parallel, group, "sp" if sp else "hp")
     try:
-        rn = model.process(latent.view(1, M, -1))
+        rn = model.process(latent.reshape(1, hi - lo, -1), slab=(rank, R) if sp else (0, 1))
     finally:
         tblock.set_head_parallel(False)
-    rn = all_reduce_backward(rn.reshape(M, -1), group)
+    rn = rn.reshape(hi - lo, -1)
+    rn = all_gather_forward(rn, group) if sp else all_reduce_backward(rn, group)
     if dec.decoder_strategy == "reverse":            # flip of the *bidirectional* encoder graph (magno.py:263-273)
         bi = enc_edges if enc.encoder_strategy == "bidirectional" else \
             local_encoder_edges("bidirectional", pos, lat, dec.gno_radius, dec.k_neighbors, group)
@@ -188,17 +283,27 @@ def sharded_forward(model, batch_local, tokens_pos, n_total: int, group=None, en
     return _apply_node_mlp(dec.projection, dec.mlp_type, out)
 
 
-def allreduce_partial_grads(model, group=None):
-    """GNO-side parameters see only this rank's points -> SUM their grads.  Everything computed on REPLICATED data
-    already holds the total gradient on every rank and is left alone: the transformer (processor, patch_linear) and the
-    encoder's geometric-embedding MLP / recovery layer, which run on the all-reduced latent tokens."""
-    replicated = ("processor.", "patch_linear.", "encoder.geoembed.", "encoder.recovery.")
-    bufs = [p.grad for n, p in model.named_parameters() if p.grad is not None and not n.startswith(replicated)]
+def allreduce_partial_grads(model, group=None, mode: Optional[str] = None):
+    """SUM the parameter gradients that are partial on every rank, in ONE flat all-reduce.  "sp": all of them (GNO-side
+    parameters see the local points, everything else the local token slab).  "hp": only the GNO side; what ran on
+    REPLICATED data (processor, patch_linear, encoder geoembed MLP / recovery) already holds the total."""
+    mode = mode or _DEFAULT["mode"]
+    if mode == "sp" and dist.get_world_size(group) > 1:
+        heads = model.processor.encoder_layers[0].attn if len(model.processor.encoder_layers) else model.processor.middle_layer.attn
+        R = dist.get_world_size(group)
+        if (model.D // model.patch_size) % R or heads.num_heads % R or heads.num_kv_heads % R:
+            mode = "hp"
+    replicated = ("processor.", "patch_linear.", "encoder.geoembed.", "encoder.recovery.") if mode == "hp" else ()
+    bufs = [p.grad for n, p in model.named_parameters() if p.grad is not None and not (replicated and n.startswith(replicated))]
     if not bufs:
         return
     flat = torch.cat([b.reshape(-1) for b in bufs])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    torch._foreach_copy_(bufs, [flat[o:o + b.numel()].view_as(b) for o, b in zip(_offsets(bufs), bufs)])
+
+
+def _offsets(bufs):
     off = 0
     for b in bufs:
-        b.copy_(flat[off: off + b.numel()].view_as(b))
+        yield off
         off += b.numel()

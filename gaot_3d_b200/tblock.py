@@ -30,11 +30,19 @@ BF16 = torch.bfloat16
 # attention core -- two thirds of its time at S = 16384 -- splits by heads with no communication before it (q/k/v of a head
 # come from the replicated activations): rank r runs heads [r H/R, (r+1) H/R), the head outputs are all-gathered (8 MB bf16
 # per layer) before the replicated o_proj, and in the backward each rank differentiates its heads and dqkv is all-gathered.
-_HEAD_PARALLEL = {"group": None, "on": False}
+#
+# Sequence-parallel mode ("sp", round 2): the whole block runs on this rank's S/R token slab -- norms, every GEMM, SwiGLU --
+# and only the attention core needs the full sequence: the bf16 [q|k|v] projections go through ONE all-to-all into the
+# head-sharded layout (rank r receives all S tokens of its H/R heads; the projection weight rows are grouped by destination
+# rank when they are cast, so the send buffer is a plain [R, S/R, W] transpose of the GEMM output), the tcgen05 attention
+# kernels run unchanged on [S, H/R heads], and a second all-to-all brings the head outputs back to token slabs.  The backward
+# mirrors it (dO forth, d[q|k|v] back).  Nothing is replicated; weight gradients are partial sums over the local tokens and
+# are all-reduced once per step by the caller (shard.allreduce_partial_grads).
+_HEAD_PARALLEL = {"group": None, "on": False, "mode": "hp"}
 
 
-def set_head_parallel(on: bool, group=None) -> None:
-    _HEAD_PARALLEL["on"], _HEAD_PARALLEL["group"] = bool(on), group
+def set_head_parallel(on: bool, group=None, mode: str = "hp") -> None:
+    _HEAD_PARALLEL["on"], _HEAD_PARALLEL["group"], _HEAD_PARALLEL["mode"] = bool(on), group, mode
 
 
 def _head_shard(num_heads: int, num_kv_heads: int):
@@ -46,8 +54,18 @@ def _head_shard(num_heads: int, num_kv_heads: int):
     grp = _HEAD_PARALLEL["group"]
     R = dist.get_world_size(grp)
     if R == 1 or num_heads % R or num_kv_heads % R:
+        if _HEAD_PARALLEL["mode"] == "sp" and R > 1:
+            raise NotImplementedError("sequence-parallel transformer: head counts must be divisible by the number of ranks")
         return None
-    return dist.get_rank(grp), R, grp
+    return dist.get_rank(grp), R, grp, _HEAD_PARALLEL["mode"]
+
+
+def _all_to_all(send: torch.Tensor, grp) -> torch.Tensor:
+    """[R, ...] -> [R, ...]: block j goes to rank j, block i of the result came from rank i."""
+    import torch.distributed as dist
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=grp)
+    return recv
 
 
 def head_slices(qkv: torch.Tensor, r: int, R: int, H: int, Hkv: int, d: int) -> torch.Tensor:
@@ -167,8 +185,19 @@ class _BlockFn(torch.autograd.Function):
             wob = torch.empty(wo.shape, dtype=BF16, device=dev)
             w2b = torch.empty(w2.shape, dtype=BF16, device=dev)
             wsk = torch.empty(skip_w.shape, dtype=BF16, device=dev) if skip is not None else None
-            _cast_many([(wq, wqkv[:nq]), (wk, wqkv[nq:nq + nkv]), (wv, wqkv[nq + nkv:]), (wo, wob), (w1, w13[:F]), (w3, w13[F:]),
-                        (w2, w2b)] + ([(skip_w, wsk)] if skip is not None else []))
+            sp = hp is not None and hp[3] == "sp"
+            if sp:      # projection rows grouped by destination rank: [q heads of r | k heads of r | v heads of r] for r = 0..R-1
+                assert B == 1, "sequence-parallel block: one example per step"
+                R_ = hp[1]
+                qa, ka = nq // R_, nkv // R_
+                Wd = qa + 2 * ka
+                qkv_casts = []
+                for j in range(R_):
+                    qkv_casts += [(wq[j * qa:(j + 1) * qa], wqkv[j * Wd:j * Wd + qa]), (wk[j * ka:(j + 1) * ka], wqkv[j * Wd + qa:j * Wd + qa + ka]),
+                                  (wv[j * ka:(j + 1) * ka], wqkv[j * Wd + qa + ka:(j + 1) * Wd])]
+            else:
+                qkv_casts = [(wq, wqkv[:nq]), (wk, wqkv[nq:nq + nkv]), (wv, wqkv[nq + nkv:])]
+            _cast_many(qkv_casts + [(wo, wob), (w1, w13[:F]), (w3, w13[F:]), (w2, w2b)] + ([(skip_w, wsk)] if skip is not None else []))
             if skip is not None:
                 s2d = f32(skip).view(M, -1)
                 x_in = _linear_fwd_raw(x2d, s2d, wsk, f32(skip_b) if skip_b is not None else None, None)
@@ -179,20 +208,28 @@ class _BlockFn(torch.autograd.Function):
             h1, _, rstd1 = _rmsnorm_fwd(x_in, n1, eps, False)
             qkv = _linear_fwd_raw(h1, None, wqkv, None, None, BF16)
             Ha, Hkva = H, Hkv                                                   # heads this rank runs through the attention core
-            if hp is not None:
-                r, R, grp = hp
+            Sa, Ma = S, M                                                       # sequence length / rows the attention core sees
+            if sp:
+                r, R, grp, _ = hp
+                Ha, Hkva = H // R, Hkv // R
+                Sa = Ma = R * M                                                 # every rank holds S/R tokens; the core sees all S
+                qkv = _all_to_all(qkv.view(M, R, Wd).transpose(0, 1).contiguous(), grp).view(Ma, Wd)
+            elif hp is not None:
+                r, R, grp, _ = hp
                 Ha, Hkva = H // R, Hkv // R
                 qkv = head_slices(qkv, r, R, H, Hkv, d)
-            packed = torch.empty(lib.gaot_attn_packed_bytes(B, S, Ha, Hkva, d), dtype=torch.uint8, device=dev)
-            o = torch.empty(M, Ha * d, dtype=BF16, device=dev)
-            o32 = torch.empty(M, Ha * d, dtype=torch.float32, device=dev)    # unrounded copy: the backward's D = rowsum(dO * O)
-            lse = torch.empty(B, Ha, S, dtype=torch.float32, device=dev)
+            packed = torch.empty(lib.gaot_attn_packed_bytes(B, Sa, Ha, Hkva, d), dtype=torch.uint8, device=dev)
+            o = torch.empty(Ma, Ha * d, dtype=BF16, device=dev)
+            o32 = torch.empty(Ma, Ha * d, dtype=torch.float32, device=dev)   # unrounded copy: the backward's D = rowsum(dO * O)
+            lse = torch.empty(B, Ha, Sa, dtype=torch.float32, device=dev)
             fr = None if freqs is None else f32(freqs)
             with ops._timed("attn_fwd", dev):
-                check(lib.gaot_attn_fused_forward(_p(qkv), qkv.stride(0), B, S, Ha, Hkva, d, _p(fr), float(p_drop), int(seed),
+                check(lib.gaot_attn_fused_forward(_p(qkv), qkv.stride(0), B, Sa, Ha, Hkva, d, _p(fr), float(p_drop), int(seed),
                                                   _p(packed), _p(o), _p(o32), _p(lse), _stream(dev)), "attn_fused_forward")
             del qkv
-            if hp is not None:
+            if sp:                                                              # head outputs back to token slabs: [M, H*d]
+                o = _all_to_all(o.view(R, M, Ha * d), grp).transpose(0, 1).reshape(M, H * d)
+            elif hp is not None:
                 o = torch.cat(_gather_cols(o, hp[1], hp[2]), dim=1)            # [M, H*d]: every rank's heads, in head order
             h = _linear_fwd_raw(o, None, wob, None, x_in)                       # x + attn(norm(x))
             h2b, h2, rstd2 = _rmsnorm_fwd(h, n2, eps, True)
@@ -241,23 +278,37 @@ class _BlockFn(torch.autograd.Function):
             del dh_b
             nq, nkv = H * d, Hkv * d
             Ha, Hkva = H, Hkv
-            if hp is not None:
-                r, R, grp = hp
+            Sa, Ma = S, M
+            sp = hp is not None and hp[3] == "sp"
+            if sp:
+                r, R, grp, _ = hp
+                Ha, Hkva = H // R, Hkv // R
+                Sa = Ma = R * M
+                do = _all_to_all(do.view(M, R, Ha * d).transpose(0, 1).contiguous(), grp).view(Ma, Ha * d)
+            elif hp is not None:
+                r, R, grp, _ = hp
                 Ha, Hkva = H // R, Hkv // R
                 do = do[:, r * Ha * d:(r + 1) * Ha * d].contiguous()
-            dqkv = torch.empty(M, (Ha + 2 * Hkva) * d, dtype=BF16, device=dev)
-            wsb = lib.gaot_attn_fused_backward_workspace_bytes(B, S, Ha, d)
+            Wd = (Ha + 2 * Hkva) * d
+            dqkv = torch.empty(Ma, Wd, dtype=BF16, device=dev)
+            wsb = lib.gaot_attn_fused_backward_workspace_bytes(B, Sa, Ha, d)
             ws = _ws(wsb, dev)
             with ops._timed("attn_bwd", dev):
-                check(lib.gaot_attn_fused_backward(_p(packed), _p(o32), _p(do), _p(lse), B, S, Ha, Hkva, d, _p(fr), p_drop, seed,
+                check(lib.gaot_attn_fused_backward(_p(packed), _p(o32), _p(do), _p(lse), B, Sa, Ha, Hkva, d, _p(fr), p_drop, seed,
                                                    _p(ws), wsb, _p(dqkv), dqkv.stride(0), _stream(dev)), "attn_fused_backward")
             del do, ws
-            if hp is not None:                                                  # [dq_l | dk_l | dv_l] of every rank -> [dq | dk | dv]
+            if sp:                                                              # d[q|k|v] of my heads, all tokens -> my tokens, all heads
+                dqkv = _all_to_all(dqkv.view(R, M, Wd), grp).transpose(0, 1).reshape(M, R * Wd)
+            elif hp is not None:                                                # [dq_l | dk_l | dv_l] of every rank -> [dq | dk | dv]
                 dqkv = merge_head_slices(_gather_cols(dqkv, hp[1], hp[2]), H, Hkv, d)
             dh1 = _linear_bwd_x_raw(dqkv, wqkv, f32)
             dwqkv = torch.empty(nq + 2 * nkv, Hd, dtype=f32, device=dev)
             _linear_bwd_w_raw(dqkv, h1, dwqkv)
             del dqkv
+            if sp:                                                              # rank-grouped rows -> [dWq; dWk; dWv]
+                g3 = dwqkv.view(R, Wd, Hd)
+                qa, ka = Ha * d, Hkva * d
+                dwqkv = torch.cat([g3[:, :qa].reshape(nq, Hd), g3[:, qa:qa + ka].reshape(nkv, Hd), g3[:, qa + ka:].reshape(nkv, Hd)])
             dx_in, dn1 = _rmsnorm_bwd(dh1, x_in, rstd1, n1, dh)
             del dh1, dh
             dskip = dwsk = dbsk = None

@@ -39,6 +39,8 @@ int  gaot_abi_version(void);
 /* number of kernel launches issued by this library since load / last reset (bench.py gpu_launches) */
 int64_t gaot_launch_count(void);
 void gaot_launch_count_reset(void);
+/* launches of this library's kernels that a CUDA-graph replay issued on the caller's behalf (counted at capture time) */
+void gaot_launch_count_add(int64_t n);
 /* optional CUDA-event timing of the main kernels on their launching stream; summary lines are
  * "kernel_name calls total_ms total_algorithmic_work" (work = bytes for HBM-bound kernels, FLOPs
  * for tensor-bound ones).  enable(on) also clears the records. */
