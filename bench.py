@@ -243,9 +243,12 @@ class Job:
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.host[0])
         self.samples_per_step = world if mode == "ddp" else 1
 
-    def set_tier(self, gno_precision, node_mlp):
+    def set_tier(self, gno_precision, node_mlp, transformer="bf16"):
         self.G.set_gno_precision(gno_precision)
         self.G.set_node_mlp_mode(NODE_MLP[node_mlp])
+        if node_mlp == "fp32":
+            self.G.set_node_mlp_tf32(False)           # strict fp32 library GEMMs (the mode switch only ever turns TF32 on)
+        self.G.set_transformer_precision(transformer)
         self.gno_precision, self.node_mlp = gno_precision, node_mlp
 
     def step(self, sample):
@@ -337,20 +340,29 @@ def kernel_table(lib, job, steps, pk):
 
 
 def cublas_bars(dev, S, hidden, ffn):
-    """cuBLAS (torch.matmul, bf16) beside this library's tcgen05 GEMMs on the step's shapes, same events, same operands."""
+    """cuBLAS (torch.matmul, bf16) beside this library's tcgen05 GEMMs on the step's shapes: same operands, both timed as
+    graph-replayed back-to-back launches (inputs stay L2-resident for both)."""
     from gaot_3d_b200 import ops
     out = {}
 
-    def t(fn, n=30):
-        for _ in range(5):
+    def t(fn, n=20, reps=5):
+        """kernel time per call: n calls recorded into ONE CUDA graph (no host launch cost on either side), replayed reps times"""
+        for _ in range(3):
             fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(n):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(n):
-            fn()
+        for _ in range(reps):
+            g.replay()
         e1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / n
+        return e0.elapsed_time(e1) / (n * reps)
 
     for name, (M, N, K) in {"qkv": (S, 3 * hidden, hidden), "o_proj": (S, hidden, hidden), "ffn_w13": (S, 2 * ffn, hidden),
                             "ffn_w2": (S, hidden, ffn), "skip_proj": (S, hidden, 2 * hidden)}.items():
@@ -606,6 +618,14 @@ def main():
                 ms32 = job.timed(max(3, args.steps // 2)) / max(3, args.steps // 2)
                 extras["fp32_gno_tier"] = {"ms_per_step": ms32, "value": 1e3 / ms32, "unit": "samples/s",
                                            "note": "GNO edge MLP + node MLPs in strict fp32 (rtol 1e-5 tier); transformer bf16 operands in both tiers"}
+                # the strict tier end to end: transformer through the reference's own fp32 library calls as well (rtol 1e-5 tier,
+                # tests/test_gpu_model.py::test_model_golden_fp32_tier)
+                job.set_tier("fp32", "fp32", transformer="fp32")
+                job.warm(2)
+                ms32s = job.timed(3) / 3
+                extras["fp32_strict_tier"] = {"ms_per_step": ms32s, "value": 1e3 / ms32s, "unit": "samples/s",
+                                              "note": "everything fp32: this library's fp32 graph / GNO / lifting kernels, transformer as fp32 cuBLAS GEMMs + "
+                                                      "fp32 F.scaled_dot_product_attention (what the reference runs on a GPU, attn.py:100-128)"}
                 job.set_tier(args.gno_precision, args.node_mlp)
             extras["cublas_bars"] = cublas_bars(dev, S, wl["hidden"], wl["ffn"])
             job.close()

@@ -55,6 +55,10 @@ _SIGS = {
     "gaot_pointnet_workspace_bytes": (c_size_t, []),
     "gaot_pointnet_forward": (c_int, [P, c_int64, P, c_int64, P, P, P, c_int, P, P, P]),
     "gaot_pointnet_backward": (c_int, [P, c_int64, P, c_int64, P, P, P, c_int, P, P, P, c_size_t, P, P]),
+    "gaot_node_linear_supported": (c_int, [c_int32, c_int32]),
+    "gaot_node_linear_workspace_bytes": (c_size_t, [c_int32, c_int32]),
+    "gaot_node_linear_forward": (c_int, [P, c_int64, c_int32, c_int32, P, P, P, P]),
+    "gaot_node_linear_backward": (c_int, [P, P, c_int64, c_int32, c_int32, P, P, c_size_t, P, P, P, P]),
     "gaot_node_mlp2_supported": (c_int, [c_int32, c_int32, c_int32]),
     "gaot_node_mlp2_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "gaot_node_mlp2_forward": (c_int, [P, c_int64, c_int32, c_int32, c_int32, P, P, P, P, P, P]),

@@ -568,7 +568,9 @@ constexpr int W_MMA = NSW, W_LOAD = NSW + 1, THREADS = (NSW + 2) * 32;
 }
 
 // EMU = how many of every 32 softmax elements take the polynomial exponential (0, 4, 8, 12)
-template <bool DROP, int EMU>
+// PREF: the scores of tile j+1 are requested from TMEM as soon as tile j's registers are consumed (their load latency runs under
+// the P store / fence / arrive tail of tile j)
+template <bool DROP, int EMU, bool PREF = false>
 __global__ void __launch_bounds__(fw2::THREADS, 1)
 attn_fwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const bf16* __restrict__ Vb,
                  void* __restrict__ out_v, int out_bf16, float* __restrict__ out32, float* __restrict__ lse,
@@ -664,13 +666,21 @@ attn_fwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const
         const uint32_t tO = tlane + TM_O + 48u * g;
         const uint32_t rowkey = DROP ? drop_rowkey(dc, (uint32_t)((b * H + h) * S + q)) : 0u;
         float m_used = -INFINITY, l_reg = 0.f;
+        uint32_t svr[32];
+        auto request_scores = [&](int j) {                // wait for S(j), then issue (not await) this thread's 32 columns
+            tc::mbar_wait(&bar_S[j & 1], (uint32_t)((j >> 1) & 1));
+            tc::fence_after_sync();
+            tc::tmem_ld32_nowait(tlane + (uint32_t)(j & 1) * 128u + 32u * g, svr);
+        };
+        if (PREF) request_scores(0);
         for (int j = 0; j < nkv; ++j) {
             const int s = j & 1;
             const uint32_t tS = tlane + (uint32_t)s * 128u + 32u * g;
-            tc::mbar_wait(&bar_S[s], (uint32_t)((j >> 1) & 1));
-            tc::fence_after_sync();
+            if (!PREF) request_scores(j);
+            tc::tmem_wait_ld();
             float sv[32];
-            tc::tmem_ld32(tS, sv);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) sv[c] = __uint_as_float(svr[c]);
             const int kvalid = S - (j * 128 + g * 32);   // keys >= kvalid of this group are padding
             if (kvalid < 32) {
 #pragma unroll
@@ -714,6 +724,7 @@ attn_fwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const
                 }
                 pk[c >> 1] = tc::pack_bf16(p0, p1);
             }
+            if (PREF && j + 1 < nkv) request_scores(j + 1);          // sv is dead from here on
             tc::tmem_st16(tS, pk);
             tc::tmem_wait_st();
             tc::fence_before_sync();
@@ -1051,7 +1062,10 @@ attn_bwd_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const 
 // dP' = V'dO'^T = dP - D come out of the tensor core (contraction length 48 = 32 + one hi/lo chunk + a zero chunk), so
 // an element costs one ex2, one multiply and two halves of a pack.  With dropout D is subtracted by hand (dO' carries
 // zeros) because the mask multiplies dP first.
-// TMEM (512 columns): stage s: S'^T at 128 s, dP'^T at 128 s + 64; dV 256; dK 288; dQ (two tiles in flight) 320 + 32 b.
+// TMEM (512 columns): NSTG = 3 score stages: S'^T at 128 s, dP'^T at 128 s + 64; dV 384; dK 416; dQ (two tiles in flight) 448 + 32 b.
+// Three stages (round 2; two before): the scores of step n+3 are issued when step n's P^T / dS^T are written, so the compute warps have
+// two steps of scores ahead of them and the ~500-cycle chain [last warp arrives -> dV, dK -> scores -> commit] no longer sits between
+// consecutive steps (ncu r01g: 14 % of the compute warps' samples were the wait for the next scores, tensor pipe 33 %, XU 44 %).
 namespace bw2 {
 constexpr int D = 32;
 constexpr int NLB = 3;                              // Q / dO tile buffers
@@ -1062,12 +1076,15 @@ constexpr int DS_B = 128 * 128 * 2;                 // 32 KB: dS^T of one query 
 constexpr int OFF_K = 0, OFF_V = TILE_B, OFF_Q = 2 * TILE_B, OFF_DO = (2 + NLB) * TILE_B, OFF_PT = (2 + 2 * NLB) * TILE_B;
 constexpr int OFF_DS = OFF_PT + 2 * PT_B, OFF_STG = OFF_DS + 2 * DS_B;
 constexpr int SMEM = OFF_STG + 4 * 4096;            // 212992 B
-constexpr uint32_t TM_DV = 256, TM_DK = 288, TM_DQ = 320;
 }
 
 // PADK: the sequence has padding keys (S % 128 != 0) -> per-element validity select; EMU: of every 32 exponentials this many
 // run as the FMA-pipe polynomial (ex2_poly)
-template <int NCW, bool DROP, bool PADK = true, int EMU = 0>
+// DBG (timing experiments only, results are wrong when non-zero): 1 = no dQ products, 2 = no dS^T shared-memory stores, 4 = no MUFU (multiply instead
+// of ex2), 8 = no dV / dK products, 16 = no dQ drain
+// PREF: the compute warps request the scores of step n+1 from TMEM as soon as the registers of step n are consumed, so the
+// tcgen05.ld latency runs under the store / fence / arrive tail of step n instead of in front of step n+1's exponentials
+template <int NCW, bool DROP, bool PADK = true, int EMU = 0, int NSTG = 2, int DBG = 0, bool PREF = false>
 __global__ void __launch_bounds__((NCW + 6) * 32, 1)
 attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const bf16* __restrict__ Vb,
                  const bf16* __restrict__ dOb, const float* __restrict__ Dvec,
@@ -1079,8 +1096,11 @@ attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const
     static_assert(NCW == 16, "a thread's 16 queries must be exactly one K16 step of the TMEM A operands");
     constexpr int CQ = D / CG;                       // dK / dV columns per compute thread in the epilogue
     constexpr int W_DRAIN = NCW, W_MMA = NCW + 4, W_LOAD = NCW + 5;
+    // NSTG score stages of 128 TMEM columns (S'^T | dP'^T of one 64-query step), then dV, dK and two dQ tiles: 512 columns at NSTG = 3
+    constexpr uint32_t TM_DV = 128u * NSTG, TM_DK = TM_DV + 32u, TM_DQ = TM_DV + 64u;
+    static_assert(NSTG == 2 || NSTG == 3, "score stages");
     extern __shared__ __align__(1024) uint8_t sm[];
-    __shared__ uint64_t bar_S[2], bar_acc[2], bar_cmp[2], bar_load[NLB], bar_dq[2];
+    __shared__ uint64_t bar_S[NSTG], bar_acc[2], bar_cmp[NSTG], bar_load[NLB], bar_dq[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float D_s[DROP ? NLB : 1][128];       // DROP only (zero-filled for padding queries)
     __shared__ __align__(16) uint32_t rk_s[DROP ? NLB : 1][128];   // DROP only: per-query row keys
@@ -1094,9 +1114,9 @@ attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
     if (tid == 32) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            tc::mbar_init(&bar_S[i], 1); tc::mbar_init(&bar_acc[i], 1); tc::mbar_init(&bar_cmp[i], NCW); tc::mbar_init(&bar_dq[i], 4);
-        }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&bar_acc[i], 1); tc::mbar_init(&bar_dq[i], 4); }
+#pragma unroll
+        for (int i = 0; i < NSTG; ++i) { tc::mbar_init(&bar_S[i], 1); tc::mbar_init(&bar_cmp[i], NCW); }
 #pragma unroll
         for (int i = 0; i < NLB; ++i) tc::mbar_init(&bar_load[i], DROP ? 34 : 1);
         tc::mbar_fence_init();
@@ -1162,7 +1182,7 @@ attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const
             const tc::Desc mdS = tc::mnmajor(sbase + OFF_DS, 128);
             auto issue_scores = [&](int n) {          // contraction over 48 columns: 32 + the statistics chunk + a zero chunk
                 const uint32_t off = ((n >> 1) % NLB) * TILE_B + (n & 1) * 64 * 16;
-                const uint32_t tS = tmem + (uint32_t)(n & 1) * 128u;
+                const uint32_t tS = tmem + (uint32_t)(n % NSTG) * 128u;
 #pragma unroll
                 for (int s = 0; s < 3; ++s)
                     tc::mma_bf16(tS, kK.adv(s * KS).u64(), kQ.adv(off + s * KS).u64(), idesc64, s > 0);
@@ -1170,35 +1190,36 @@ attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const
                 for (int s = 0; s < 3; ++s)
                     tc::mma_bf16(tS + 64, kV.adv(s * KS).u64(), kdO.adv(off + s * KS).u64(), idesc64, s > 0);
             };
-            tc::mbar_wait(&bar_load[0], 0);
-            tc::fence_after_sync();
-            issue_scores(0); tc::mma_commit(&bar_S[0]);
-            issue_scores(1); tc::mma_commit(&bar_S[1]);
+            for (int n = 0; n < NSTG && n < nsteps; ++n) {                      // the first NSTG steps' scores
+                if ((n & 1) == 0) { tc::mbar_wait(&bar_load[(n >> 1) % NLB], 0); tc::fence_after_sync(); }
+                issue_scores(n); tc::mma_commit(&bar_S[n]);
+            }
             for (int n = 0; n < nsteps; ++n) {
-                const int i = n >> 1, hq = n & 1, s = n & 1;
-                tc::mbar_wait(&bar_cmp[s], (uint32_t)((n >> 1) & 1));           // P^T / dS^T of step n written, stage s drained
+                const int i = n >> 1, hq = n & 1, s = n % NSTG;
+                tc::mbar_wait(&bar_cmp[s], (uint32_t)((n / NSTG) & 1));         // P^T / dS^T of step n written, stage s drained
                 tc::fence_after_sync();
                 const uint32_t off = (i % NLB) * TILE_B + hq * 64 * 16;
                 const uint32_t tS = tmem + (uint32_t)s * 128u;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)     // dV[key,d] += P^T[key, 16 q] dO[16 q, d]   (A = packed P^T in the stage's S' columns)
+                for (int k = 0; k < ((DBG & 8) ? 0 : 4); ++k)     // dV[key,d] += P^T[key, 16 q] dO[16 q, d]   (A = packed P^T in the stage's S' columns)
                     tc::mma_bf16_ts(tmem + TM_DV, tS + 16u * k, mdO.adv(off + k * tc::KSTEP_MN).u64(), idescKM, (n | k) != 0);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)     // dK[key,d] += dS^T[key, 16 q] Q'[16 q, d]  (A = packed dS^T in the stage's dP' columns)
+                for (int k = 0; k < ((DBG & 8) ? 0 : 4); ++k)     // dK[key,d] += dS^T[key, 16 q] Q'[16 q, d]  (A = packed dS^T in the stage's dP' columns)
                     tc::mma_bf16_ts(tmem + TM_DK, tS + 64u + 16u * k, mQ.adv(off + k * tc::KSTEP_MN).u64(), idescKM, (n | k) != 0);
-                if (n + 2 < nsteps) {             // overwrites the stage the two products above read: ordered behind them
-                    if (hq == 0) tc::mbar_wait(&bar_load[(i + 1) % NLB], (uint32_t)(((i + 1) / NLB) & 1));
-                    issue_scores(n + 2);
+                if (n + NSTG < nsteps) {          // overwrites the stage the two products above read: ordered behind them
+                    const int n2 = n + NSTG, i2 = n2 >> 1;
+                    if ((n2 & 1) == 0) { tc::mbar_wait(&bar_load[i2 % NLB], (uint32_t)((i2 / NLB) & 1)); tc::fence_after_sync(); }
+                    issue_scores(n2);
                     tc::mma_commit(&bar_S[s]);
                 }
                 if (hq == 1) {
                     if (i >= 2) { tc::mbar_wait(&bar_dq[i & 1], (uint32_t)(((i - 2) >> 1) & 1)); tc::fence_after_sync(); }
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)   // dQ[q,d] = dS[q, key] K[key, d] over the 128 queries of the tile
+                    for (int k = 0; k < ((DBG & 1) ? 0 : 8); ++k)   // dQ[q,d] = dS[q, key] K[key, d] over the 128 queries of the tile
                         tc::mma_bf16(tmem + TM_DQ + (uint32_t)(i & 1) * 32u, mdS.adv((i & 1) * DS_B + k * tc::KSTEP_MN).u64(),
                                      mK.adv(k * tc::KSTEP_MN).u64(), idescMM, k > 0);
                 }
-                tc::mma_commit(&bar_acc[s]);
+                tc::mma_commit(&bar_acc[hq]);
             }
         }
         __syncwarp();
@@ -1216,6 +1237,7 @@ attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const
             __syncwarp();
             if (lane == 0) { tc::mbar_arrive(&bar_dq[i & 1]); tc::bulk_wait_read0(); }   // staging block free again
             __syncwarp();
+            if (DBG & 16) continue;
             {
                 // Row `lane` is 128 contiguous bytes (the bulk reduce needs the block linear), so a straight float4 store
                 // would put all lanes of a quarter-warp on the same four banks (8-way conflict, ~1000 smem cycles per
@@ -1258,12 +1280,11 @@ attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const
         const int c0 = cg * CPT;
         const uint32_t kterm = (uint32_t)key * 0x85EBCA6Bu;
         uint8_t* const ds0 = sm + OFF_DS + (cg * (CPT / 8)) * (128 * 16) + row * 16;
-        for (int n = 0; n < nsteps; ++n) {
-            const int i = n >> 1, hq = n & 1, s = n & 1;
-            if (DROP && hq == 0) tc::mbar_wait(&bar_load[i % NLB], (uint32_t)((i / NLB) & 1));   // D / row keys of the tile
-            tc::mbar_wait(&bar_S[s], (uint32_t)((n >> 1) & 1));
+        uint32_t r0[CPT], r1[CPT];
+        auto request_scores = [&](int n) {            // wait for the scores of step n, then issue (not await) their TMEM loads
+            const int s = n % NSTG;
+            tc::mbar_wait(&bar_S[s], (uint32_t)((n / NSTG) & 1));
             tc::fence_after_sync();
-            uint32_t r0[CPT], r1[CPT];
             if constexpr (CPT == 16) {
                 tc::tmem_ld16_nowait(tlane + (uint32_t)s * 128u + c0, r0);
                 tc::tmem_ld16_nowait(tlane + (uint32_t)s * 128u + 64u + c0, r1);
@@ -1271,6 +1292,12 @@ attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const
                 tc::tmem_ld32_nowait(tlane + (uint32_t)s * 128u + c0, r0);
                 tc::tmem_ld32_nowait(tlane + (uint32_t)s * 128u + 64u + c0, r1);
             }
+        };
+        if (PREF) request_scores(0);
+        for (int n = 0; n < nsteps; ++n) {
+            const int i = n >> 1, hq = n & 1, s = n % NSTG;
+            if (DROP && hq == 0) tc::mbar_wait(&bar_load[i % NLB], (uint32_t)((i / NLB) & 1));   // D / row keys of the tile
+            if (!PREF) request_scores(n);
             tc::tmem_wait_ld();
             uint4 pk[CPT / 8], dk[CPT / 8];
 #pragma unroll
@@ -1280,7 +1307,7 @@ attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const
                 for (int c = 0; c < 8; ++c) {
                     const int cc = c8 * 8 + c;
                     const bool emu = ((cc + 1) * EMU) / 32 > (cc * EMU) / 32;
-                    const float e = emu ? ex2_poly(__uint_as_float(r0[cc])) : ex2_approx(__uint_as_float(r0[cc]));
+                    const float e = (DBG & 4) ? __uint_as_float(r0[cc]) * 0.001f : (emu ? ex2_poly(__uint_as_float(r0[cc])) : ex2_approx(__uint_as_float(r0[cc])));
                     p[c] = valid_k ? e : 0.f;                              // padding keys: P = dS = 0
                     if (DROP) {
                         const int qi = hq * 64 + c0 + cc;
@@ -1296,6 +1323,7 @@ attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const
                 dk[c8].x = tc::pack_bf16(ds[0], ds[1]); dk[c8].y = tc::pack_bf16(ds[2], ds[3]);
                 dk[c8].z = tc::pack_bf16(ds[4], ds[5]); dk[c8].w = tc::pack_bf16(ds[6], ds[7]);
             }
+            if (PREF && n + 1 < nsteps) request_scores(n + 1);      // r0 / r1 are dead from here on
             // P^T and dS^T go back INTO the TMEM columns their scores came from (this thread owns them) as packed bf16
             // pairs: they are the A operands of dV / dK.  dS^T also goes to shared memory for dQ = dS K (transposed use).
             {
@@ -1307,12 +1335,15 @@ attn_bwd2_kernel(const bf16* __restrict__ Qb, const bf16* __restrict__ Kb, const
                 for (int c8 = 0; c8 < CPT / 8; ++c8) { a[c8 * 4] = dk[c8].x; a[c8 * 4 + 1] = dk[c8].y; a[c8 * 4 + 2] = dk[c8].z; a[c8 * 4 + 3] = dk[c8].w; }
                 tc::tmem_st8(tlane + (uint32_t)s * 128u + 64u + c0, a);
             }
-            if (n >= 2) tc::mbar_wait(&bar_acc[s], (uint32_t)(((n >> 1) - 1) & 1));   // dQ of tile i-2 has read this dS^T buffer
+            if (n >= 2) tc::mbar_wait(&bar_acc[hq], (uint32_t)(((n >> 1) - 1) & 1));  // dQ of tile i-2 has read this dS^T buffer
             uint8_t* dst = ds0 + (i & 1) * DS_B + hq * 8 * (128 * 16);
 #pragma unroll
-            for (int c8 = 0; c8 < CPT / 8; ++c8) *reinterpret_cast<uint4*>(dst + c8 * (128 * 16)) = dk[c8];
+            if (!(DBG & 2)) {
+#pragma unroll
+                for (int c8 = 0; c8 < CPT / 8; ++c8) *reinterpret_cast<uint4*>(dst + c8 * (128 * 16)) = dk[c8];
+            }
             tc::tmem_wait_st();
-            tc::fence_async_smem();
+            if (!(DBG & 2)) tc::fence_async_smem();
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&bar_cmp[s]);
@@ -1427,11 +1458,18 @@ static int attn_launch_fwd(const AttnWs& w, int64_t B, int64_t S, int H, int Hkv
 #define GAOT_FWD2(DR, EM)                                                                                              \
     do { GAOT_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<DR, EM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fw2::SMEM)); \
          attn_fwd2_kernel<DR, EM><<<grid, fw2::THREADS, fw2::SMEM, st>>>(w.Qb, w.Kb, w.Vb, out, out_bf16, out32, lse, (int)S, H, Hkv, dc); } while (0)
+        // score prefetch measured SLOWER in the forward (0.854 vs 0.659 ms at S = 16384, r02f): kept for A/B only
+        static const int fpref = getenv("GAOT_ATTN_FWD_PREF") ? atoi(getenv("GAOT_ATTN_FWD_PREF")) : 0;
+#define GAOT_FWD2P(EM)                                                                                                 \
+    do { GAOT_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<false, EM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fw2::SMEM)); \
+         attn_fwd2_kernel<false, EM, true><<<grid, fw2::THREADS, fw2::SMEM, st>>>(w.Qb, w.Kb, w.Vb, out, out_bf16, out32, lse, (int)S, H, Hkv, dc); } while (0)
         if (drop) { if (emu >= 8) GAOT_FWD2(true, 8); else GAOT_FWD2(true, 0); }          // the dropout variant keeps all-MUFU unless asked
+        else if (fpref) { if (emu >= 8) GAOT_FWD2P(8); else if (emu >= 4) GAOT_FWD2P(4); else GAOT_FWD2P(0); }
         else if (emu >= 12) GAOT_FWD2(false, 12);
         else if (emu >= 8) GAOT_FWD2(false, 8);
         else if (emu >= 4) GAOT_FWD2(false, 4);
         else GAOT_FWD2(false, 0);
+#undef GAOT_FWD2P
 #undef GAOT_FWD2
         GAOT_LAUNCH_CHECK();
         return GAOT_OK;
@@ -1484,15 +1522,40 @@ static int attn_launch_bwd(const AttnWs& w, const float* lse, int64_t B, int64_t
         // GAOT_ATTN_BWD_EMU = 0 / 4 / 8 (of every 32 exponentials on the FMA pipe); sequences without padding keys skip the
         // per-element validity select
         static const int bemu = getenv("GAOT_ATTN_BWD_EMU") ? atoi(getenv("GAOT_ATTN_BWD_EMU")) : 0;
-#define GAOT_BWD2_LAUNCH4(PK, EM)                                                                                      \
-    do { GAOT_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<16, false, PK, EM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bw2::SMEM)); \
-         attn_bwd2_kernel<16, false, PK, EM><<<grid, (16 + 6) * 32, bw2::SMEM, st>>>(w.Qb, w.Kb, w.Vb, w.dOb, w.Dvec, w.dQacc, w.dKh, w.dVh, \
-                                                                                    (int)S, H, Hkv, scale, scale_dk, dc); } while (0)
+        // measured at S = 16384 (profiles/r02f_attn_variants.txt): 2 stages 1.164 ms; 3 stages 1.188; 2 stages + score prefetch 1.429;
+        // 3 stages + score prefetch 1.109 (default).  GAOT_ATTN_BWD_STAGES / GAOT_ATTN_BWD_PREF pick the others for A/B timing.
+        static const int bstg = getenv("GAOT_ATTN_BWD_STAGES") ? atoi(getenv("GAOT_ATTN_BWD_STAGES")) : 3;
+        static const int bdbg = getenv("GAOT_ATTN_BWD_DBG") ? atoi(getenv("GAOT_ATTN_BWD_DBG")) : 0;        // ablation timing (wrong results)
+        static const int bpref = getenv("GAOT_ATTN_BWD_PREF") ? atoi(getenv("GAOT_ATTN_BWD_PREF")) : (bstg == 3 ? 1 : 0);
+#define GAOT_BWD2_LAUNCH6(NS)                                                                                          \
+    do { GAOT_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<16, false, false, 0, NS, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bw2::SMEM)); \
+         attn_bwd2_kernel<16, false, false, 0, NS, 0, true><<<grid, (16 + 6) * 32, bw2::SMEM, st>>>(w.Qb, w.Kb, w.Vb, w.dOb, w.Dvec, w.dQacc, w.dKh, w.dVh, \
+                                                                                                   (int)S, H, Hkv, scale, scale_dk, dc); } while (0)
+#define GAOT_BWD2_LAUNCH5(DB)                                                                                          \
+    do { GAOT_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<16, false, false, 0, 2, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bw2::SMEM)); \
+         attn_bwd2_kernel<16, false, false, 0, 2, DB><<<grid, (16 + 6) * 32, bw2::SMEM, st>>>(w.Qb, w.Kb, w.Vb, w.dOb, w.Dvec, w.dQacc, w.dKh, w.dVh, \
+                                                                                             (int)S, H, Hkv, scale, scale_dk, dc); } while (0)
+#define GAOT_BWD2_LAUNCH4(PK, EM, NS)                                                                                  \
+    do { GAOT_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<16, false, PK, EM, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bw2::SMEM)); \
+         attn_bwd2_kernel<16, false, PK, EM, NS><<<grid, (16 + 6) * 32, bw2::SMEM, st>>>(w.Qb, w.Kb, w.Vb, w.dOb, w.Dvec, w.dQacc, w.dKh, w.dVh, \
+                                                                                        (int)S, H, Hkv, scale, scale_dk, dc); } while (0)
         if (drop) GAOT_BWD2_LAUNCH(16, true);
         else if (S % 128 != 0) GAOT_BWD2_LAUNCH(16, false);
-        else if (bemu >= 8) GAOT_BWD2_LAUNCH4(false, 8);
-        else if (bemu >= 4) GAOT_BWD2_LAUNCH4(false, 4);
-        else GAOT_BWD2_LAUNCH4(false, 0);
+        else if (bdbg) {
+            switch (bdbg) {
+                case 1: GAOT_BWD2_LAUNCH5(1); break;   case 2: GAOT_BWD2_LAUNCH5(2); break;   case 3: GAOT_BWD2_LAUNCH5(3); break;
+                case 4: GAOT_BWD2_LAUNCH5(4); break;   case 8: GAOT_BWD2_LAUNCH5(8); break;   case 16: GAOT_BWD2_LAUNCH5(16); break;
+                case 11: GAOT_BWD2_LAUNCH5(11); break; case 27: GAOT_BWD2_LAUNCH5(27); break; case 31: GAOT_BWD2_LAUNCH5(31); break;
+                default: GAOT_BWD2_LAUNCH5(0); break;
+            }
+        }
+        else if (bpref) { if (bstg == 3) GAOT_BWD2_LAUNCH6(3); else GAOT_BWD2_LAUNCH6(2); }
+        else if (bstg == 3) GAOT_BWD2_LAUNCH4(false, 0, 3);
+        else if (bemu >= 8) GAOT_BWD2_LAUNCH4(false, 8, 2);
+        else if (bemu >= 4) GAOT_BWD2_LAUNCH4(false, 4, 2);
+        else GAOT_BWD2_LAUNCH4(false, 0, 2);
+#undef GAOT_BWD2_LAUNCH6
+#undef GAOT_BWD2_LAUNCH5
 #undef GAOT_BWD2_LAUNCH4
 #undef GAOT_BWD2_LAUNCH
         GAOT_LAUNCH_CHECK();

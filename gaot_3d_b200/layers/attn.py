@@ -63,6 +63,9 @@ def _cfg_dict(obj) -> dict:
 
 def _lin(mod: nn.Linear, x, residual=None, x2=None):
     """nn.Linear forward on the tcgen05 dense kernel (parameters stay in the nn.Linear, so state_dict keys match)."""
+    if x.is_cuda and ops.transformer_precision() == "fp32":      # strict tier: the reference's own fp32 library GEMM
+        y = F.linear(x if x2 is None else torch.cat([x, x2], dim=-1), mod.weight, mod.bias)
+        return y if residual is None else y + residual
     if x.is_cuda and ops.linear_supported(mod.in_features, mod.out_features) and (x2 is None or x.shape[-1] % 64 == 0):
         return ops.linear(x, mod.weight, mod.bias, residual=residual, x2=x2)
     if not x.is_cuda:
@@ -80,6 +83,33 @@ class RotaryEmbedding(nn.Module):
     def __init__(self, dim, theta=10000.0):
         super().__init__()
         self.freqs = nn.Parameter(1.0 / (theta ** (torch.arange(0, dim, 2)[: dim // 2].float() / dim)), requires_grad=False)
+
+
+def _rope_fp32(t: torch.Tensor, freqs: torch.Tensor) -> torch.Tensor:
+    """1-D rotary embedding over the sequence axis of [B, h, S, d] (rotary_embedding_torch semantics as the reference uses
+    them, attn.py:119-120: positions 0..S-1, angle f_i on the adjacent pair (2i, 2i+1), out = t cos + rotate_half(t) sin)."""
+    S = t.shape[-2]
+    ang = torch.arange(S, device=t.device, dtype=torch.float32)[:, None] * freqs.to(torch.float32)[None, :]     # [S, d/2]
+    cos, sin = ang.cos().repeat_interleave(2, dim=-1), ang.sin().repeat_interleave(2, dim=-1)
+    pair = t.reshape(*t.shape[:-1], t.shape[-1] // 2, 2)
+    rot = torch.stack((-pair[..., 1], pair[..., 0]), dim=-1).reshape(t.shape)
+    return t * cos + rot * sin
+
+
+def _sdpa_fp32(q, k, v, num_heads, num_kv_heads, freqs, dropout_p):
+    """Strict-FP32 tier of the attention core: the reference's own sequence of library calls (attn.py:110-128)."""
+    B, S, _ = q.shape
+    d = q.shape[-1] // num_heads
+    q = q.view(B, S, num_heads, d).transpose(1, 2)
+    k = k.view(B, S, num_kv_heads, d).transpose(1, 2)
+    v = v.view(B, S, num_kv_heads, d).transpose(1, 2)
+    if freqs is not None:
+        q, k = _rope_fp32(q, freqs), _rope_fp32(k, freqs)
+    if num_kv_heads != num_heads:
+        rep = num_heads // num_kv_heads
+        k, v = k.repeat_interleave(rep, dim=1), v.repeat_interleave(rep, dim=1)
+    o = F.scaled_dot_product_attention(q, k, v, dropout_p=dropout_p)
+    return o.transpose(1, 2).reshape(B, S, num_heads * d)
 
 
 class GroupQueryFlashAttention(nn.Module):
@@ -112,6 +142,10 @@ class GroupQueryFlashAttention(nn.Module):
         q, k, v = _lin(self.q_proj, x3), _lin(self.k_proj, x3), _lin(self.v_proj, x3)
         dp = self.atten_dropout if self.training else 0.0          # reference attn.py:122-126
         freqs = self.rotary_emb.freqs if relative_positions is not None else None
+        if ops.transformer_precision() == "fp32":
+            o = _sdpa_fp32(q, k, v, self.num_heads, self.num_kv_heads, freqs, dp)
+            res3 = None if residual is None else residual.reshape(x3.shape[0], x3.shape[1], -1)
+            return _lin(self.o_proj, o, residual=res3).reshape(*lead, x.shape[-2], -1)
         o = ops.attention(q, k, v, self.num_heads, self.num_kv_heads, rope_freqs=freqs, dropout_p=dp)
         res3 = None if residual is None else residual.reshape(x3.shape[0], x3.shape[1], -1)
         return _lin(self.o_proj, o, residual=res3).reshape(*lead, x.shape[-2], -1)
@@ -191,7 +225,7 @@ class TransformerBlock(nn.Module):
         """One-autograd-node path (tblock.py): both norms present, square block, shapes inside the kernel envelope."""
         a, f = self.attn, self.ffn
         hid = a.q_proj.in_features
-        return (FUSED_BLOCK and x.is_cuda and x.dtype == torch.float32 and self.attn_norm is not None and self.ffn_norm is not None
+        return (FUSED_BLOCK and ops.transformer_precision() == "bf16" and x.is_cuda and x.dtype == torch.float32 and self.attn_norm is not None and self.ffn_norm is not None
                 and a.q_proj.out_features == hid and a.o_proj.out_features == hid and f.w2.out_features == hid
                 and f.w1.in_features == hid and self.attn_norm.eps == self.ffn_norm.eps
                 and (not self.skip_connection or self.skip_proj.in_features == 2 * hid)

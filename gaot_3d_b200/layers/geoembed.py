@@ -34,7 +34,11 @@ class GeometricEmbedding(nn.Module):
     def statistical_features(self, source_pos, query_pos, edge_index, normalize=True):
         csr = ops.csr_of(edge_index, source_pos.shape[0], query_pos.shape[0])
         feat = ops.geo_stats(source_pos, query_pos, csr, normalize=normalize)
-        if self.input_dim == 2:        # [N, Davg, Dvar, dx, dy, (dz), l0, l1, (l2)] -> drop the padded axis
+        if self.input_dim == 2:
+            # points padded with z = 0: the 3x3 covariance has a zero row / column, its eigenvalues (+ 1e-6) in descending order
+            # are the two of the 2x2 problem followed by 1e-6, the centroid offset's z is 0 -> the reference's 7 features
+            # (geoembed.py:95-97) are columns [N, Davg, Dvar, dx, dy, l0, l1]; the z-score is per column, so selecting after it
+            # is the same as before it
             feat = feat[:, [0, 1, 2, 3, 4, 6, 7]]
         return feat
 
@@ -43,8 +47,8 @@ class GeometricEmbedding(nn.Module):
                 neighbors_counts: Optional[torch.Tensor] = None) -> torch.Tensor:
         if neighbors_counts is not None:
             raise NotImplementedError("neighbors_counts override is unused by the reference (magno.py:513-516)")
-        if self.input_dim == 2:
-            raise NotImplementedError("2-D geometric embedding: the kernels are built for 3-D coordinates")
+        if self.input_dim not in (2, 3):
+            raise NotImplementedError("geometric embedding: 2-D or 3-D coordinates")
         if self.method == "pointnet":
             return self.pointnet_features(source_pos, query_pos, edge_index)
         return self.mlp(self.statistical_features(source_pos, query_pos, edge_index))
@@ -56,6 +60,9 @@ class GeometricEmbedding(nn.Module):
             return torch.zeros(nq, self.output_dim, device=query_pos.device, dtype=query_pos.dtype)
         csr = ops.csr_of(edge_index, source_pos.shape[0], nq)
         l1, l2 = self.pointnet_mlp[0], self.pointnet_mlp[2]
-        pooled = ops.pointnet_pool(source_pos, query_pos, csr, l1.weight, l1.bias, l2.weight, l2.bias, self.pooling)
+        w1 = l1.weight
+        if self.input_dim == 2:        # the kernel reads zero-padded 3-D offsets: a zero weight column for the padded axis
+            w1 = torch.cat([w1, w1.new_zeros(w1.shape[0], 1)], dim=1)
+        pooled = ops.pointnet_pool(source_pos, query_pos, csr, w1, l1.bias, l2.weight, l2.bias, self.pooling)
         has = (csr.rowptr[1:] > csr.rowptr[:-1]).to(pooled.dtype).unsqueeze(1)
         return self.fc(pooled) * has

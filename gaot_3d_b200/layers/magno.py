@@ -74,6 +74,14 @@ def _apply_node_mlp(mlp, mlp_type, x):
         if mlp.fcs[0].bias is not None and mlp.fcs[1].bias is not None and x.dim() == 2 and \
                 ops.node_mlp2_supported(w1.shape[1], w1.shape[0], w2.shape[0]):
             return ops.node_mlp2(x, w1, mlp.fcs[0].bias, w2, mlp.fcs[1].bias)
+    # one-layer MLPs with a tiny input width (the lifting layer: raw point features -> lifting channels over every physical
+    # point) stream through a dedicated fp32 kernel in every mode: as a library GEMM the shape is all padding and its weight
+    # gradient a 10^6-row reduction
+    if x.is_cuda and getattr(mlp, "n_layers", 0) == 1 and mlp.dropout is None and x.dim() == 2 and x.dtype == torch.float32:
+        w = mlp.fcs[0].weight
+        w = w.reshape(w.shape[0], -1)
+        if ops.node_linear_supported(w.shape[1], w.shape[0]):
+            return ops.node_linear(x, w, mlp.fcs[0].bias)
     return mlp(x) if mlp_type == "linear" else mlp(x.transpose(0, 1)).transpose(0, 1)
 
 

@@ -28,6 +28,23 @@ def get_gno_precision() -> str:
     return "fp32" if _PRECISION["gno"] == 0 else "bf16"
 
 
+_TRANSFORMER = {"precision": "bf16"}
+
+
+def set_transformer_precision(name: str) -> None:
+    """'bf16' (default): the latent transformer on this library's tcgen05 kernels -- bf16 operands, fp32 accumulation, the
+    north star's rtol 2e-2 tier.  'fp32': the strict tier -- the same modules through the reference's own library calls
+    (fp32 cuBLAS GEMMs with TF32 off, fp32 F.scaled_dot_product_attention, reference attn.py:100-128), so that a whole-model
+    rtol 1e-5 comparison exists; graph build, GNO, geometric embedding stay on this library's fp32 kernels."""
+    if name not in ("bf16", "fp32"):
+        raise ValueError("transformer precision must be 'bf16' or 'fp32'")
+    _TRANSFORMER["precision"] = name
+
+
+def transformer_precision() -> str:
+    return _TRANSFORMER["precision"]
+
+
 _NODE_MLP = {"mode": "torch"}
 
 
@@ -353,6 +370,13 @@ def gno(y_pos, x_pos, f_y, csr: Csr, weights, biases, transform_type: str = "lin
         if transform_type not in _TRANSFORMS:
             raise ValueError(f"unknown transform_type {transform_type}")
         t = _TRANSFORMS[transform_type]
+    if y_pos.shape[1] == 2:
+        # 2-D coordinates (MAGNOConfig.gno_coord_dim = 2, the dataclass default): the kernels gather zero-padded 3-D points, so the
+        # first layer [h, 2 + 2 (+ C)] gets zero columns where the padded z of y and of x sit -- same products, and autograd
+        # hands the gradient of the real columns back through the concatenation
+        w0 = weights[0]
+        z = w0.new_zeros(w0.shape[0], 1)
+        weights = [torch.cat([w0[:, :2], z, w0[:, 2:4], z, w0[:, 4:]], dim=1), *weights[1:]]
     dims = [int(weights[0].shape[1])] + [int(w.shape[0]) for w in weights]
     prec = _PRECISION["gno"] if precision is None else (0 if precision == "fp32" else 1)
     return _GnoFn.apply(_pos3(y_pos), _pos3(x_pos), f_y, csr, tuple(dims), t, 0 if reduce == "mean" else 1, prec,
@@ -503,6 +527,54 @@ def node_mlp2(x, w1, b1, w2, b2):
     w1_, w2_ = w1.reshape(w1.shape[0], -1), w2.reshape(w2.shape[0], -1)
     y = _NodeMlp2Fn.apply(x, w1_, b1, w2_, b2)
     return y
+
+
+# ----------------------------------------------------------------------------- one-layer node MLP, tiny input width
+def node_linear_supported(k_in: int, c_out: int) -> bool:
+    return bool(_lib_().gaot_node_linear_supported(int(k_in), int(c_out)))
+
+
+class _NodeLinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b):
+        lib = _lib_()
+        f32 = lambda t: t.detach().to(torch.float32).contiguous()
+        xd, wd = f32(x), f32(w)
+        bd = None if b is None else f32(b)
+        n, k_in = xd.shape
+        c_out = wd.shape[0]
+        dev = xd.device
+        y = torch.empty(n, c_out, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.gaot_node_linear_forward(_p(xd), n, k_in, c_out, _p(wd), _p(bd), _p(y), _stream(dev)), "node_linear_forward")
+        ctx.save_for_backward(xd, wd)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xd, wd = ctx.saved_tensors
+        lib = _lib_()
+        n, k_in = xd.shape
+        c_out = wd.shape[0]
+        dev = xd.device
+        dy = dy.to(torch.float32).contiguous()
+        dx = torch.empty_like(xd) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(wd)
+        db = torch.empty(c_out, dtype=torch.float32, device=dev) if ctx.has_bias else None
+        wsb = lib.gaot_node_linear_workspace_bytes(k_in, c_out)
+        ws = _ws(wsb, dev)
+        with torch.cuda.device(dev):
+            check(lib.gaot_node_linear_backward(_p(xd), _p(dy), n, k_in, c_out, _p(wd), _p(ws), wsb, _p(dx), _p(dw), _p(db),
+                                                _stream(dev)), "node_linear_backward")
+        return dx, dw, db
+
+
+def node_linear(x, w, b=None):
+    """y = x W^T + b for [N, k_in <= 16] rows in fp32 as one streaming kernel each way: the encoder's lifting layer (reference
+    magno.py:421-424, :540-545).  Weight [c_out, k_in] (a kernel-size-1 Conv1d weight reshaped is the same)."""
+    _need_cuda(x, w, b)
+    return _NodeLinearFn.apply(x, w.reshape(w.shape[0], -1), b)
 
 
 # ----------------------------------------------------------------------------- dense layers (nn.Linear)

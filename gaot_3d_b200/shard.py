@@ -150,16 +150,19 @@ def apply_global_radius_cap(lat_idx: torch.Tensor, phys_idx: torch.Tensor, num_l
     the subset that survives the GLOBAL cap: edge ordinal (edges of lower ranks + local ordinal) < cap."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    counts = torch.bincount(lat_idx, minlength=num_latent)
-    allc = [torch.empty_like(counts) for _ in range(world)]
-    dist.all_gather(allc, counts, group=group)
-    before = torch.zeros_like(counts)
-    for r in range(rank):
-        before += allc[r]
+    counts = _count(lat_idx, num_latent)
+    allc = torch.empty(world, num_latent, dtype=counts.dtype, device=counts.device)
+    _all_gather(allc.view(-1), counts, group)
+    before = allc[:rank].sum(dim=0)                               # edges of the lower ranks, per latent
     start = torch.cumsum(counts, 0) - counts                      # edges are grouped by ascending latent
     ordinal = torch.arange(lat_idx.numel(), device=lat_idx.device) - start[lat_idx]
     keep = (before[lat_idx] + ordinal) < cap
     return lat_idx[keep], phys_idx[keep]
+
+
+def _count(idx: torch.Tensor, n: int) -> torch.Tensor:
+    """bincount without the host synchronisation torch.bincount makes (it reads the maximum back)."""
+    return torch.zeros(n, dtype=torch.long, device=idx.device).scatter_add_(0, idx, torch.ones_like(idx))
 
 
 def local_encoder_edges(strategy: str, phys_local, latent_pos, radius: float, k: int, group=None,
@@ -250,7 +253,11 @@ def sharded_forward(model, batch_local, tokens_pos, n_total: int, group=None, en
         enc_edges = local_encoder_edges(enc.encoder_strategy, pos, lat, enc.gno_radius, enc.k_neighbors, group)
     lifted = _apply_node_mlp(enc.lifting, enc.mlp_type, enc._features(batch_local))
     part = enc.gno(y_pos=pos, x_pos=lat, edge_index=enc_edges, f_y=lifted, reduce="sum")       # partial sums [M,C]
-    cnt = torch.bincount(enc_edges[1], minlength=M).to(part.dtype)
+    if pos.is_cuda:        # the CSR the GNO kernel just built (cached on the edge tensor) already holds the per-token counts
+        rp = ops.csr_of(enc_edges, pos.shape[0], M).rowptr
+        cnt = (rp[1:] - rp[:-1]).to(part.dtype)
+    else:
+        cnt = _count(enc_edges[1], M).to(part.dtype)
     fused = torch.cat([part, cnt.unsqueeze(1)], dim=1)                # sums and counts travel in ONE collective
     lo, hi = (rank * (M // R), (rank + 1) * (M // R)) if sp else (0, M)
     tot = reduce_scatter_forward(fused, group) if sp else all_reduce_forward(fused, group)

@@ -202,6 +202,19 @@ int gaot_node_mlp2_backward(const float* x, const float* d_y, int64_t n, int32_t
                             const float* w1, const float* b1, const float* w2, void* ws, size_t ws_bytes, float* d_x,
                             float* d_params, void* stream);
 
+/* ------------------------------------------------------------------ one-layer node MLP with a tiny input width
+ * y = W x + b on every row of x [n, k_in], k_in <= 16, c_out <= 64, fp32 FMA (both precision tiers): the encoder's lifting
+ *   layer (reference src/model/layers/magno.py:421-424 `self.lifting`, applied at :540-545; LinearChannelMLP mlp.py:327-335 /
+ *   ChannelMLP :283-305 with one layer).  W [c_out, k_in] row-major (a kernel-size-1 Conv1d weight has the same layout), b may
+ *   be null.  Streaming kernels: 4 (k_in + c_out) bytes per row each way; the weight gradient is a fixed-order (deterministic)
+ *   two-stage reduction.  d_x and d_b may be null. */
+int gaot_node_linear_supported(int32_t k_in, int32_t c_out);
+size_t gaot_node_linear_workspace_bytes(int32_t k_in, int32_t c_out);
+int gaot_node_linear_forward(const float* x, int64_t n, int32_t k_in, int32_t c_out, const float* w, const float* b, float* y,
+                             void* stream);
+int gaot_node_linear_backward(const float* x, const float* d_y, int64_t n, int32_t k_in, int32_t c_out, const float* w,
+                              void* ws, size_t ws_bytes, float* d_x, float* d_w, float* d_b, void* stream);
+
 /* ------------------------------------------------------------------ latent attention
  * Replaces rotary_emb + F.scaled_dot_product_attention of reference
  *   src/model/layers/attn.py:110-128.  q [B,S,H*d], k,v [B,S,Hkv*d] float32 (projection

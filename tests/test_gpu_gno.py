@@ -330,3 +330,48 @@ def test_gno_attentional_transform_tensor_core(attention_type):
         if n == "key_proj.bias":
             continue                                            # identically zero (softmax shift invariance)
         assert rl2(p.grad, params[n].grad) < 2e-2, (n, rl2(p.grad, params[n].grad))
+
+
+def test_two_dimensional_coordinates():
+    """gno_coord_dim = 2 (the MAGNOConfig default, reference magno.py:23): graph build, integral transform, statistical and
+    PointNet geometric embedding on [N, 2] coordinates against the (dimension-generic, reference-pinned) oracle."""
+    import gaot_3d_b200 as G
+    from gaot_3d_b200.layers import GeometricEmbedding, IntegralTransform
+    torch.manual_seed(3)
+    rng = np.random.default_rng(5)
+    phys = rng.uniform(-1, 1, (6000, 2)).astype(np.float32)
+    gx = np.linspace(-1, 1, 24, dtype=np.float32)
+    lat = np.stack(np.meshgrid(gx, gx, indexing="ij"), -1).reshape(-1, 2)
+    r, C = 0.11, 16
+    P, L = torch.from_numpy(phys), torch.from_numpy(lat)
+    for strategy, dec in (("radius", False), ("knn", True), ("bidirectional", False)):
+        ref_e = og.get_neighbor_strategy_np(strategy, phys, None, lat, None, r, 2, dec)
+        e = G.get_neighbor_strategy(strategy, P.to(DEV), None, L.to(DEV), None, r, 2, dec)
+        assert np.array_equal(e.cpu().numpy(), ref_e), f"2-D {strategy} edges"
+    ei = torch.from_numpy(og.get_neighbor_strategy_np("radius", phys, None, lat, None, r, 2, False))    # [phys; latent]
+    it = IntegralTransform(channel_mlp_layers=[4, 32, C]).to(DEV)
+    f = torch.randn(len(phys), C)
+    fd = f.to(DEV).requires_grad_(True)
+    out = it(P.to(DEV), L.to(DEV), ei.to(DEV), fd)
+    ws = [l.weight.detach().cpu().clone().requires_grad_(True) for l in it.channel_mlp.fcs]
+    bs = [l.bias.detach().cpu().clone().requires_grad_(True) for l in it.channel_mlp.fcs]
+    fr = f.clone().requires_grad_(True)
+    ref = ogno.integral_transform(P, L, ei, fr, ws, bs)
+    close(out, ref, what="2-D gno forward")
+    go = torch.randn_like(ref)
+    out.backward(go.to(DEV))
+    ref.backward(go)
+    close(fd.grad, fr.grad, rtol=2e-5, atol_rel=1e-5, what="2-D d_f")
+    for i, l in enumerate(it.channel_mlp.fcs):
+        assert l.weight.grad.shape == ws[i].shape
+        close(l.weight.grad, ws[i].grad, rtol=1e-4, atol_rel=2e-5, what=f"2-D dW{i}")
+    ge = GeometricEmbedding(2, 8).to(DEV)
+    feat = ge.statistical_features(P.to(DEV), L.to(DEV), ei.to(DEV))
+    reff = ogno.geo_statistical_features(P, L, ei)
+    assert feat.shape == reff.shape == (len(lat), 7)
+    close(feat, reff, rtol=1e-3, atol_rel=1e-4, what="2-D statistical features")
+    gp = GeometricEmbedding(2, 8, method="pointnet").to(DEV)
+    st = {k: v.detach().cpu() for k, v in gp.state_dict().items()}
+    refp = ogno.geo_pointnet_embedding(P, L, ei, st["pointnet_mlp.0.weight"], st["pointnet_mlp.0.bias"], st["pointnet_mlp.2.weight"],
+                                       st["pointnet_mlp.2.bias"], st["fc.0.weight"], st["fc.0.bias"], "max")
+    close(gp(P.to(DEV), L.to(DEV), ei.to(DEV)), refp, rtol=1e-4, atol_rel=1e-5, what="2-D pointnet")

@@ -62,3 +62,47 @@ def test_projection_module_uses_the_fused_kernel_when_asked():
         # shapes outside the envelope keep the torch path
         other = _node_mlp(mlp_type, 64, 32).to(DEV)
         assert _apply_node_mlp(other, mlp_type, torch.randn(10, 64, device=DEV)).shape == (10, 32)
+
+
+@pytest.mark.parametrize("n,k_in,c_out,bias", [(0, 6, 32, True), (1, 6, 32, True), (1000, 5, 16, True), (40001, 6, 32, False),
+                                               (300000, 6, 32, True), (5000, 16, 64, True), (777, 3, 48, True), (2049, 1, 1, True)])
+def test_node_linear_forward_backward(n, k_in, c_out, bias):
+    """The lifting layer's streaming kernel (reference magno.py:421-424, :540-545; Linear forward mlp.py:327-335) against the
+    same Linear in fp64: fp32 FMA in both directions -> the FP32 tier's rtol 1e-5 (of the output / gradient scale)."""
+    from gaot_3d_b200 import ops
+    torch.manual_seed(n + k_in)
+    x = torch.randn(n, k_in)
+    w, b = torch.randn(c_out, k_in) / k_in ** 0.5, (torch.randn(c_out) * 0.3 if bias else None)
+    go = torch.randn(n, c_out)
+    ref_in = [t.double().requires_grad_(True) for t in (x, w)] + ([b.double().requires_grad_(True)] if bias else [])
+    yr = F.linear(ref_in[0], ref_in[1], ref_in[2] if bias else None)
+    yr.backward(go.double())
+    dev_in = [t.to(DEV).requires_grad_(True) for t in (x, w)] + ([b.to(DEV).requires_grad_(True)] if bias else [])
+    y = ops.node_linear(dev_in[0], dev_in[1], dev_in[2] if bias else None)
+    assert y.shape == (n, c_out)
+    y.backward(go.to(DEV))
+    if n == 0:
+        assert all(float(a.grad.abs().sum()) == 0.0 for a in dev_in[1:])
+        return
+    assert rel(y, yr) < 1e-5, ("y", rel(y, yr))
+    for name, a, r in zip(("dx", "dW", "db"), dev_in, ref_in):
+        assert rel(a.grad, r.grad) < 2e-5, (name, rel(a.grad, r.grad))
+    dev2 = [t.to(DEV).requires_grad_(True) for t in (x, w)] + ([b.to(DEV).requires_grad_(True)] if bias else [])
+    y2 = ops.node_linear(dev2[0], dev2[1], dev2[2] if bias else None)
+    y2.backward(go.to(DEV))
+    assert torch.equal(y, y2) and all(torch.equal(a.grad, c.grad) for a, c in zip(dev_in, dev2)), "not deterministic"
+
+
+def test_lifting_module_uses_the_streaming_kernel():
+    """MAGNOEncoder.lifting through _apply_node_mlp: both node-MLP flavours, default (strict fp32) mode."""
+    from gaot_3d_b200 import ops
+    from gaot_3d_b200.layers.magno import _apply_node_mlp, _node_mlp
+    torch.manual_seed(0)
+    x = torch.randn(5000, 6, device=DEV)
+    for mlp_type in ("linear", "channel"):
+        mlp = _node_mlp(mlp_type, 6, 32).to(DEV)
+        ref = mlp(x) if mlp_type == "linear" else mlp(x.transpose(0, 1)).transpose(0, 1)
+        ops.reset_launch_count()
+        out = _apply_node_mlp(mlp, mlp_type, x)
+        assert ops.launch_count() >= 1, "the lifting layer did not launch the library kernel"
+        assert rel(out, ref) < 1e-5, (mlp_type, rel(out, ref))

@@ -93,6 +93,20 @@ def test_restatements_match_reference_modules():
                                         st["pointnet_mlp.2.bias"], st["fc.0.weight"], st["fc.0.bias"], pooling)
         assert torch.allclose(a, b, rtol=1e-6, atol=1e-7), pooling
         assert float(b[torch.bincount(ei2[1], minlength=200) == 0].abs().max()) == 0.0
+    # 2-D coordinates (MAGNOConfig.gno_coord_dim defaults to 2, reference magno.py:23): the restatements are dimension-generic
+    y2, x2 = y[:, :2].contiguous(), x[:, :2].contiguous()
+    it = ref.integral_transform.IntegralTransform(channel_mlp_layers=[4, 32, 16])
+    f = torch.randn(800, 16)
+    b = ogno.integral_transform(y2, x2, ei, f, [l.weight for l in it.channel_mlp.fcs], [l.bias for l in it.channel_mlp.fcs])
+    assert torch.allclose(it(y2, x2, ei, f), b, rtol=1e-6, atol=1e-7), "2-D integral transform"
+    ge2 = ref.geoembed.GeometricEmbedding(2, 8)
+    a = ge2._compute_statistical_features_pyg(y2, x2, ei)
+    assert a.shape[1] == 7 and torch.allclose(a, ogno.geo_statistical_features(y2, x2, ei), rtol=1e-5, atol=1e-6), "2-D statistics"
+    gp2 = ref.geoembed.GeometricEmbedding(2, 8, method="pointnet")
+    st = gp2.state_dict()
+    b = ogno.geo_pointnet_embedding(y2, x2, ei2, st["pointnet_mlp.0.weight"], st["pointnet_mlp.0.bias"], st["pointnet_mlp.2.weight"],
+                                    st["pointnet_mlp.2.bias"], st["fc.0.weight"], st["fc.0.bias"], "max")
+    assert torch.allclose(gp2(y2, x2, ei2), b, rtol=1e-6, atol=1e-7), "2-D pointnet"
     # scatter_native mean with empty segments
     src, idx = torch.randn(50, 4), torch.randint(0, 9, (50,))
     assert torch.allclose(ref.scatter_native.scatter_native(src, idx, dim=0, dim_size=12, reduce="mean"), ogno.scatter_mean(src, idx, 12))
