@@ -55,6 +55,9 @@ _SIGS = {
     "gaot_pointnet_workspace_bytes": (c_size_t, []),
     "gaot_pointnet_forward": (c_int, [P, c_int64, P, c_int64, P, P, P, c_int, P, P, P]),
     "gaot_pointnet_backward": (c_int, [P, c_int64, P, c_int64, P, P, P, c_int, P, P, P, c_size_t, P, P]),
+    "gaot_a2a_put": (c_int, [P, P, c_int32, c_int32, c_int64, P]),
+    "gaot_p2p_put": (c_int, [P, P, c_int32, c_int32, c_int64, c_int32, P]),
+    "gaot_p2p_reduce": (c_int, [P, c_int32, c_int64, c_int64, P, P]),
     "gaot_node_linear_supported": (c_int, [c_int32, c_int32]),
     "gaot_node_linear_workspace_bytes": (c_size_t, [c_int32, c_int32]),
     "gaot_node_linear_forward": (c_int, [P, c_int64, c_int32, c_int32, P, P, P, P]),

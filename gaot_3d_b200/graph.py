@@ -66,16 +66,71 @@ def _per_example(fn, x, y, batch_x, batch_y):
     return torch.cat(rows), torch.cat(cols)
 
 
+# ----------------------------------------------------------------------------- sample-keyed search cache
+# One forward asks for the same search several times: the decoder's 'reverse' graph is the flip of the *bidirectional* encoder
+# graph (reference magno.py:263-273 rebuilds it from scratch), a knn decoder repeats the knn encoder's search, and every scale of a
+# multi-scale model repeats the scale-independent knn part (magno.py:502, :711 loop over scales).  INSIDE ONE FORWARD (a
+# `sample_scope()`, opened by GAOT3D.forward and shard.sharded_forward) results are kept in a small LRU keyed by the identity AND
+# version counter of the position / batch tensors (an in-place update of the coordinates misses) plus the search parameters; the
+# scope's exit drops everything, so nothing is ever reused from one sample / training step to the next (the online graph build
+# stays inside every step) and nothing outlives the forward.  The entry holds references to its inputs, so a data pointer cannot
+# be recycled while it is cached.  The cached tensors are handed out as they are: treat a returned edge_index as read-only.
+_CACHE = {"on": True, "max": 8, "entries": {}, "depth": 0}
+
+
+def set_graph_cache(on: bool = True, max_entries: int = 8) -> None:
+    """Process-wide switch of the per-forward search cache (MAGNOConfig.use_graph_cache, unused by the reference, names the intent)."""
+    _CACHE["on"], _CACHE["max"] = bool(on), int(max_entries)
+    _CACHE["entries"].clear()
+
+
+class sample_scope:
+    """Context manager around the graph builds of ONE sample (one model forward); nests."""
+
+    def __enter__(self):
+        _CACHE["depth"] += 1
+        return self
+
+    def __exit__(self, *exc):
+        _CACHE["depth"] -= 1
+        if _CACHE["depth"] == 0:
+            _CACHE["entries"].clear()
+        return False
+
+
+def _tkey(t: Optional[torch.Tensor]):
+    return None if t is None else (t.data_ptr(), t._version, tuple(t.shape), t.dtype, t.device.index)
+
+
+def _cached(kind, tensors, params, build):
+    if not _CACHE["on"] or _CACHE["depth"] == 0:
+        return build()
+    key = (kind, tuple(_tkey(t) for t in tensors), params)
+    ent = _CACHE["entries"].get(key)
+    if ent is not None:
+        _CACHE["entries"][key] = _CACHE["entries"].pop(key)          # most recently used last
+        return ent[1]
+    out = build()
+    while len(_CACHE["entries"]) >= _CACHE["max"]:
+        _CACHE["entries"].pop(next(iter(_CACHE["entries"])))
+    _CACHE["entries"][key] = (tensors, out)
+    return out
+
+
 def radius_graph(x, y, r, batch_x=None, batch_y=None, max_num_neighbors: int = PYG_MAX_NUM_NEIGHBORS):
     """torch_geometric.nn.radius(x, y, r, batch_x, batch_y): returns [2,E], row 0 = y index, row 1 = x index."""
-    ry, cx = _per_example(lambda a, b: ops.radius(a, b, r, max_num_neighbors), x, y, batch_x, batch_y)
-    return torch.stack([ry, cx])
+    def build():
+        ry, cx = _per_example(lambda a, b: ops.radius(a, b, r, max_num_neighbors), x, y, batch_x, batch_y)
+        return torch.stack([ry, cx])
+    return _cached("radius", (x, y, batch_x, batch_y), (float(r), int(max_num_neighbors)), build)
 
 
 def knn_graph(x, y, k, batch_x=None, batch_y=None):
     """torch_geometric.nn.knn(x, y, k, batch_x, batch_y): returns [2, ny*k], row 0 = y index, row 1 = x index."""
-    ry, cx = _per_example(lambda a, b: ops.knn(a, b, k), x, y, batch_x, batch_y)
-    return torch.stack([ry, cx])
+    def build():
+        ry, cx = _per_example(lambda a, b: ops.knn(a, b, k), x, y, batch_x, batch_y)
+        return torch.stack([ry, cx])
+    return _cached("knn", (x, y, batch_x, batch_y), (int(k),), build)
 
 
 def _tag(ei: torch.Tensor, query_sorted: bool) -> torch.Tensor:
@@ -97,9 +152,11 @@ def _encoder_edges(strategy, phys_pos, batch_phys, latent_pos, batch_latent, rad
     if strategy == "radius":       # latent tokens as centres: raw [latent, phys] -> flip
         return _tag(radius_graph(phys_pos, latent_pos, radius, batch_phys, batch_latent).flip(0).contiguous(), True)
     if strategy == "bidirectional":
-        e_knn = knn_graph(latent_pos, phys_pos, k, batch_latent, batch_phys)
-        e_rad = radius_graph(phys_pos, latent_pos, radius, batch_phys, batch_latent).flip(0)
-        return _tag(_coalesced([e_knn, e_rad], n_phys, n_lat), False)
+        def build():
+            e_knn = knn_graph(latent_pos, phys_pos, k, batch_latent, batch_phys)
+            e_rad = radius_graph(phys_pos, latent_pos, radius, batch_phys, batch_latent).flip(0)
+            return _tag(_coalesced([e_knn, e_rad], n_phys, n_lat), False)
+        return _cached("enc_bidirectional", (phys_pos, latent_pos, batch_phys, batch_latent), (float(radius), int(k)), build)
     raise ValueError(f"Unknown encoder strategy: {strategy}")
 
 

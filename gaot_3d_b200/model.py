@@ -115,11 +115,13 @@ class GAOT3D(nn.Module):
                 "query_coord_pos and query_coord_batch_idx must have same length"
             assert query_coord_batch_idx.max() == num_graphs - 1, "query_coord_batch_idx does not match batch size"
             query_pos, query_batch = query_coord_pos.to(device), query_coord_batch_idx.to(device)
-        rndata = self.encoder(batch=batch, latent_tokens_pos=latent_pos, latent_tokens_batch_idx=latent_batch)
-        rndata = self.process(rndata=rndata, condition=condition)
-        flat = rndata.reshape(-1, self.node_latent_size)
-        return self.decoder(rndata_flat=flat, phys_pos_query=query_pos, batch_idx_phys_query=query_batch,
-                            latent_tokens_pos=latent_pos, latent_tokens_batch_idx=latent_batch, batch=batch)
+        from .graph import sample_scope
+        with sample_scope():       # searches repeated inside this forward (reverse decoder, knn on both sides, scales) run once
+            rndata = self.encoder(batch=batch, latent_tokens_pos=latent_pos, latent_tokens_batch_idx=latent_batch)
+            rndata = self.process(rndata=rndata, condition=condition)
+            flat = rndata.reshape(-1, self.node_latent_size)
+            return self.decoder(rndata_flat=flat, phys_pos_query=query_pos, batch_idx_phys_query=query_batch,
+                                latent_tokens_pos=latent_pos, latent_tokens_batch_idx=latent_batch, batch=batch)
 
 
 def init_model(input_size: int, output_size: int, model: str, config=None):

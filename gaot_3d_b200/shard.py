@@ -112,6 +112,11 @@ class _AllGatherFwd(torch.autograd.Function):
 
 def _reduce_scatter(out, inp, group):
     if inp.is_cuda:
+        from . import p2p
+        res = p2p.reduce_scatter(inp, group)                 # peer-memory pull-reduce (deterministic order) when available
+        if res is not None:
+            out.copy_(res)
+            return
         dist.reduce_scatter_tensor(out, inp, op=dist.ReduceOp.SUM, group=group)
     else:       # gloo (CPU tests) has no reduce_scatter: all-reduce a copy and keep the own slab
         tmp = inp.clone()
@@ -122,6 +127,11 @@ def _reduce_scatter(out, inp, group):
 
 def _all_gather(out, inp, group):
     if inp.is_cuda:
+        from . import p2p
+        res = p2p.all_gather(inp, group)
+        if res is not None:
+            out.copy_(res.view(out.shape))
+            return
         dist.all_gather_into_tensor(out, inp, group=group)
     else:
         parts = [torch.empty_like(inp) for _ in range(dist.get_world_size(group))]
@@ -220,6 +230,13 @@ def set_default_mode(mode: str) -> None:
 
 def sharded_forward(model, batch_local, tokens_pos, n_total: int, group=None, enc_edges: Optional[torch.Tensor] = None,
                     head_parallel: bool = True, mode: Optional[str] = None):
+    from .graph import sample_scope
+    with sample_scope():
+        return _sharded_forward(model, batch_local, tokens_pos, n_total, group, enc_edges, head_parallel, mode)
+
+
+def _sharded_forward(model, batch_local, tokens_pos, n_total: int, group=None, enc_edges: Optional[torch.Tensor] = None,
+                     head_parallel: bool = True, mode: Optional[str] = None):
     """GAOT3D forward on this rank's shard of ONE sample (batch of one).  Returns the local rows of
     the output [N_local, C_out].  `model` is a gaot_3d_b200.GAOT3D (single scale, use_gno=True).
     mode "sp": token-sharded processor (nothing replicated); "hp": round 1's replicated processor with a head-parallel
@@ -305,7 +322,9 @@ def allreduce_partial_grads(model, group=None, mode: Optional[str] = None):
     if not bufs:
         return
     flat = torch.cat([b.reshape(-1) for b in bufs])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    from . import p2p
+    if not (flat.dtype == torch.float32 and p2p.all_reduce_(flat, group)):       # two-shot over peer memory, else NCCL
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     torch._foreach_copy_(bufs, [flat[o:o + b.numel()].view_as(b) for o, b in zip(_offsets(bufs), bufs)])
 
 

@@ -61,11 +61,23 @@ def _head_shard(num_heads: int, num_kv_heads: int):
 
 
 def _all_to_all(send: torch.Tensor, grp) -> torch.Tensor:
-    """[R, ...] -> [R, ...]: block j goes to rank j, block i of the result came from rank i."""
+    """[R, ...] -> [R, ...]: block j goes to rank j, block i of the result came from rank i.  Over NVLink peer memory (p2p.py:
+    one store kernel + the symmetric allocation's barrier) when the node allows it, else ncclSend/ncclRecv groups.  The peer
+    path returns a view of a symmetric buffer that the second next exchange overwrites: every caller below consumes or copies
+    it before then."""
     import torch.distributed as dist
+    from . import p2p
+    out = p2p.all_to_all(send, grp)
+    if out is not None:
+        return out
     recv = torch.empty_like(send)
     dist.all_to_all_single(recv, send, group=grp)
     return recv
+
+
+def a2a_backend(grp=None) -> str:
+    from . import p2p
+    return p2p.backend(grp)
 
 
 def head_slices(qkv: torch.Tensor, r: int, R: int, H: int, Hkv: int, d: int) -> torch.Tensor:

@@ -215,6 +215,20 @@ int gaot_node_linear_forward(const float* x, int64_t n, int32_t k_in, int32_t c_
 int gaot_node_linear_backward(const float* x, const float* d_y, int64_t n, int32_t k_in, int32_t c_out, const float* w,
                               void* ws, size_t ws_bytes, float* d_x, float* d_w, float* d_b, void* stream);
 
+/* ------------------------------------------------------------------ all-to-all over peer memory (intra-sample sharding)
+ * Data movement of one all-to-all among the `world` GPUs of a node: block j (block_bytes, a multiple of 16) of `send` is stored
+ *   into slot `rank` of peer j's receive buffer, peer_recv[j] being THIS process's mapping of that buffer (symmetric memory /
+ *   CUDA IPC); peer_recv is a HOST array of `world` device pointers.  One kernel, every destination in parallel.  The caller
+ *   orders the stores before the consumers with a cross-rank barrier on the same stream (tblock.py).  New with the sharded
+ *   path: the reference has no intra-sample parallelism (src/trainer/stat.py:431-436 is sample-level DDP). */
+int gaot_a2a_put(const void* send, const void* const* peer_recv, int32_t rank, int32_t world, int64_t block_bytes, void* stream);
+/* the same store kernel; bcast != 0: the ONE block of `send` goes to slot `rank` of every peer (all-gather) */
+int gaot_p2p_put(const void* send, const void* const* peer_recv, int32_t rank, int32_t world, int64_t block_bytes, int32_t bcast,
+                 void* stream);
+/* out[i] = sum_{r = 0..world-1} peer_src[r][offset_floats + i], i < n_floats (fp32, fixed rank order -> deterministic): the reduce
+ *   half of a reduce-scatter / two-shot all-reduce, pulled from the peers' symmetric buffers.  Offset and count in multiples of 4. */
+int gaot_p2p_reduce(const void* const* peer_src, int32_t world, int64_t offset_floats, int64_t n_floats, float* out, void* stream);
+
 /* ------------------------------------------------------------------ latent attention
  * Replaces rotary_emb + F.scaled_dot_product_attention of reference
  *   src/model/layers/attn.py:110-128.  q [B,S,H*d], k,v [B,S,Hkv*d] float32 (projection

@@ -140,3 +140,35 @@ def test_host_buffer_entry_points():
     rc = lib.gaot_knn_host(lat.ctypes.data, len(lat), phys.ctypes.data, len(phys), 2, oy.ctypes.data, ox.ctypes.data, ctypes.byref(E))
     assert rc == 0, lib.gaot_last_error()
     assert np.array_equal(np.stack([oy[:E.value], ox[:E.value]]), og.knn_np(lat, phys, 2, workers=-1))
+
+
+def test_sample_scope_cache_reuses_searches_without_changing_results():
+    """Inside one forward (graph.sample_scope) the reverse decoder graph reuses the bidirectional encoder build and repeated knn
+    searches run once; outside a scope nothing is cached; an in-place change of the coordinates misses."""
+    import gaot_3d_b200 as G
+    from gaot_3d_b200 import graph, ops
+    DEV = torch.device("cuda:0")
+    phys = torch.from_numpy(synth.surface_cloud(20000, seed=4)).to(DEV)
+    lat = torch.from_numpy(synth.latent_grid((12, 12, 12))).to(DEV)
+    r, k = 0.2, 2
+    ref_enc = G.get_neighbor_strategy("bidirectional", phys, None, lat, None, r, k, False)
+    ref_dec = G.get_neighbor_strategy("reverse", phys, None, lat, None, r, k, True)
+    ops.reset_launch_count()
+    G.get_neighbor_strategy("reverse", phys, None, lat, None, r, k, True)
+    cold = ops.launch_count()
+    with graph.sample_scope():
+        e = G.get_neighbor_strategy("bidirectional", phys, None, lat, None, r, k, False)
+        ops.reset_launch_count()
+        d = G.get_neighbor_strategy("reverse", phys, None, lat, None, r, k, True)
+        warm = ops.launch_count()
+        e_knn = G.get_neighbor_strategy("knn", phys, None, lat, None, r, k, False)
+        ops.reset_launch_count()
+        d_knn = G.get_neighbor_strategy("knn", phys, None, lat, None, r, k, True)
+        assert ops.launch_count() == 0, "the decoder's knn search must come from the cache"
+        phys.add_(0.0)                                     # bumps the version counter: the next search is a miss
+        ops.reset_launch_count()
+        G.get_neighbor_strategy("knn", phys, None, lat, None, r, k, True)
+        assert ops.launch_count() > 0
+    assert torch.equal(e, ref_enc) and torch.equal(d, ref_dec) and torch.equal(d_knn, e_knn.flip(0))
+    assert warm == 0 and cold > 0, (warm, cold)
+    assert not graph._CACHE["entries"], "the scope's exit must drop every entry"

@@ -57,7 +57,9 @@ def test_model_golden_fp32_tier(tag):
     kernels, the transformer through the reference's own fp32 library calls (set_transformer_precision('fp32')).  Truth is the
     oracle in fp64; the bar is elementwise |ours - truth| <= 1e-5 * max|truth| + what the reference's own fp32 evaluation
     (the golden output, computed by the unmodified reference modules on CPU) is away from that truth -- gradients likewise,
-    per parameter tensor in relative L2 (<= 1e-4: sums over 1e3..1e4 points in a different order)."""
+    per parameter tensor in relative L2: <= 1e-4 (sums over 1e3..1e4 points in a different order) + twice what the SAME
+    arithmetic in fp32 on the CPU (the oracle in fp32) is away from the fp64 truth for that tensor (the q / k projection
+    gradients cancel heavily: measured r02g 1.0e-4 .. 1.2e-4 there, everything else < 1e-4)."""
     import gaot_3d_b200 as G
     from tests.test_gpu_model_variants import _leaf_state
     g = torch.load(os.path.join(GOLD, "model_golden.pt"))[tag]
@@ -82,6 +84,8 @@ def test_model_golden_fp32_tier(tag):
     y64 = omodel.gaot3d_forward(sd, cfg, keep_graph=True, dtype=torch.float64, pos=g["pos"], feats=[g["pos"], g["c"]],
                                 latent_pos=g["tokens_pos"])
     y64.pow(2).mean().backward()
+    sd32 = _leaf_state(m)
+    omodel.gaot3d_forward(sd32, cfg, keep_graph=True, pos=g["pos"], feats=[g["pos"], g["c"]], latent_pos=g["tokens_pos"]).pow(2).mean().backward()
     scale = y64.detach().abs().max().item()
     ref_err = (g["out"].double() - y64.detach()).abs().max().item()
     err = (y.detach().cpu().double() - y64.detach()).abs().max().item()
@@ -93,6 +97,7 @@ def test_model_golden_fp32_tier(tag):
             continue
         gr = sd[n].grad.double()
         rel = ((p.grad.detach().cpu().double() - gr).norm() / gr.norm().clamp(min=1e-30)).item()
-        if rel > 1e-4:
-            bad.append(f"{n}: {rel:.2e}")
+        own = ((sd32[n].grad.double() - gr).norm() / gr.norm().clamp(min=1e-30)).item()
+        if rel > 1e-4 + 2.0 * own:
+            bad.append(f"{n}: {rel:.2e} (fp32 CPU evaluation: {own:.2e})")
     assert not bad, f"{tag} fp32-tier gradient parity: " + "; ".join(bad)
