@@ -606,6 +606,10 @@ def main():
                    "ms_per_step": ms_e2e / args.steps},
            "gpu_launches": launches, "cuda_graphs": bool(tgraph.enabled()), "roofline": roofline, "kernels": kernels, "gno_edges_per_s": gno}
 
+    if mode == "shard":
+        from gaot_3d_b200 import p2p
+        out["collectives"] = {"backend": p2p.backend(None), "peer_ops": sorted(p2p._OPS) if p2p.backend(None) == "p2p" else [],
+                              "note": "p2p = stores / pull-reduces over NVLink peer memory (csrc/a2a.cu) + symmetric-memory barrier; nccl = torch.distributed"}
     extras = {}
     if not args.no_extras:
         if world == 1:
@@ -680,8 +684,24 @@ def main():
             except Exception as e:  # the baseline is reporting only; never lose the GPU line
                 out["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port", "sample": f"failed: {e}"}
         emit(out)
+    # tear-down: CUDA graphs that hold NCCL kernels must go before the communicator does (destroy_process_group hung for 200 s
+    # on an 8-rank run that still held them); a watchdog ends the process if the clean shutdown does not return -- the JSON
+    # line is already out
+    try:
+        tgraph.reset()
+        torch.cuda.synchronize()
+    except Exception:
+        pass
     if world > 1:
-        dist.destroy_process_group()
+        t = threading.Timer(30.0, lambda: os._exit(0))
+        t.daemon = True
+        t.start()
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        except Exception:
+            pass
+        t.cancel()
 
 
 if __name__ == "__main__":
