@@ -111,3 +111,54 @@ def test_head_parallel_column_bookkeeping():
     import gaot_3d_b200 as G
     with pytest.raises(ValueError):
         G.set_node_mlp_mode("fast")
+
+
+def test_search_cache_scope_logic():
+    """graph._cached / sample_scope (host logic, no kernels): nothing is cached outside a scope; inside one the same tensors +
+    parameters hit, different parameters or an in-place update miss; the LRU is bounded; the outermost exit drops everything."""
+    from gaot_3d_b200 import graph
+    calls = []
+
+    def build():
+        calls.append(1)
+        return torch.zeros(2, 3, dtype=torch.long)
+
+    x, y = torch.rand(5, 3), torch.rand(4, 3)
+    graph._cached("knn", (x, y, None, None), (1,), build)
+    graph._cached("knn", (x, y, None, None), (1,), build)
+    assert len(calls) == 2 and not graph._CACHE["entries"], "no caching outside a sample scope"
+    with graph.sample_scope():
+        a = graph._cached("knn", (x, y, None, None), (1,), build)
+        with graph.sample_scope():                                  # nests
+            b = graph._cached("knn", (x, y, None, None), (1,), build)
+        assert a is b and len(calls) == 3
+        assert graph._CACHE["entries"], "the inner exit must not clear the outer scope's entries"
+        graph._cached("knn", (x, y, None, None), (2,), build)        # other parameters
+        graph._cached("radius", (x, y, None, None), (1,), build)      # other kind
+        assert len(calls) == 5
+        x.add_(1.0)                                                   # in-place update: version counter moves
+        graph._cached("knn", (x, y, None, None), (1,), build)
+        assert len(calls) == 6
+        for i in range(3, 3 + 2 * graph._CACHE["max"]):
+            graph._cached("knn", (x, y, None, None), (i,), build)
+        assert len(graph._CACHE["entries"]) <= graph._CACHE["max"]
+    assert not graph._CACHE["entries"] and graph._CACHE["depth"] == 0
+    graph.set_graph_cache(False)
+    try:
+        with graph.sample_scope():
+            n = len(calls)
+            graph._cached("knn", (x, y, None, None), (1,), build)
+            graph._cached("knn", (x, y, None, None), (1,), build)
+            assert len(calls) == n + 2
+    finally:
+        graph.set_graph_cache(True)
+
+
+def test_peer_collectives_decline_cpu_tensors():
+    """p2p.* answer None / False for anything the peer path cannot carry (CPU tensors, odd sizes): callers then use
+    torch.distributed.  No process group is needed to find that out."""
+    from gaot_3d_b200 import p2p
+    t = torch.rand(2, 8, 4)
+    assert p2p.all_to_all(t) is None and p2p.all_gather(t) is None and p2p.reduce_scatter(t) is None
+    assert p2p.all_reduce_(torch.rand(10)) is False
+    assert p2p.backend(None) == "nccl"

@@ -77,6 +77,22 @@ def _worker(rank, world, port, ret):
         std = feats.std(dim=0)
         zf = (feats - feats.mean(dim=0)) / torch.where(std < 1e-6, torch.ones_like(std), std)
         assert torch.allclose(zl, zf[lo:hi], rtol=1e-4, atol=1e-5), "global z-score"
+        # --- the token-sharded ("sp") mode's collectives as autograd functions: reduce-scatter forward <-> all-gather backward,
+        #     all-gather forward <-> reduce-scatter backward (gloo has neither natively: shard._reduce_scatter / _all_gather)
+        Mtok = 2 * world * 3
+        xp = (torch.arange(Mtok * 4, dtype=torch.float32).view(Mtok, 4) * (rank + 1)).requires_grad_(True)
+        slab = shard.reduce_scatter_forward(xp)                              # [Mtok / world, 4] = (sum_r x_r)[my slab]
+        n_s = Mtok // world
+        tot_ref = torch.arange(Mtok * 4, dtype=torch.float32).view(Mtok, 4) * sum(range(1, world + 1))
+        assert torch.equal(slab, tot_ref[rank * n_s:(rank + 1) * n_s]), "reduce-scatter forward"
+        full = shard.all_gather_forward(slab * 2.0)                          # every rank: the whole field
+        assert torch.equal(full, tot_ref * 2.0), "all-gather forward"
+        wgt = torch.arange(Mtok * 4, dtype=torch.float32).view(Mtok, 4) / 7.0 + rank    # a different consumer per rank
+        (full * wgt).sum().backward()
+        # d full is a per-rank partial -> reduce-scatter sums it over ranks for my slab; then x2; then the reduce-scatter's
+        # backward all-gathers the slab gradients: every rank's x receives the gradient of every slab
+        wsum = sum(torch.arange(Mtok * 4, dtype=torch.float32).view(Mtok, 4) / 7.0 + r for r in range(world))
+        assert torch.allclose(xp.grad, 2.0 * wsum), "sp collectives backward"
         ret[rank] = "ok"
     except Exception as e:  # pragma: no cover
         import traceback
