@@ -140,17 +140,19 @@ def run_cpu_arm(wl, steps, warmup, budget_s=150.0):
     # clouds above 1M points: the point-proportional parts (search, GNO encoder / decoder) run on a contiguous 1/ps subsample and are
     # scaled by ps (flagged `extrapolated`); the transformer does not depend on the point count
     ps = max(1, wl["n_points"] // 500_000) if wl["n_points"] > 1_000_000 else 1
+    if ps > 1:
+        budget_s = min(budget_s, 100.0)
     while True:
         i = done_w + len(times)
         pos, nrm, tgt = make_sample(dict(wl, n_points=wl["n_points"] // ps), seed=i % 4)
         # the one-off warm-up step runs 2 blocks only (it exists to page in torch / build the thread pool)
         r = cpu_step.cpu_step_seconds(pos, nrm, tgt, lat, cpu_cfg(wl, float(ps)), layers_timed=(2 if done_w < warmup else None),
-                                      search_workers=-1, seed=i, single_thread_search=(done_w >= warmup and not times))
+                                      search_workers=-1, seed=i, single_thread_search=(done_w >= warmup and not times and ps == 1))
         if done_w < warmup:
             done_w += 1
             continue
         times.append(r["seconds"])
-        last = r if "graph_single_thread" in r["parts"] or last is None else last
+        last = r if ("graph_single_thread" in r["parts"] or last is None or "graph_single_thread" not in last["parts"]) else last
         elapsed = time.perf_counter() - t_start
         if len(times) >= steps or elapsed + 1.2 * float(np.mean(times)) > budget_s:
             break
