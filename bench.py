@@ -610,6 +610,9 @@ def main():
 
     if mode == "shard":
         from gaot_3d_b200 import p2p
+        out["scaling_note"] = ("strong scaling of ONE 8M-point sample (BASELINE configs[3]); this bench's N = 1 line is a different workload "
+                               "(configs[1], 500K points) -- the N = 1 point of THIS workload is extras.n1_same_workload (rank 0 alone, same run): "
+                               "speed-up = n1_same_workload.ms_per_step / ms_per_step; the weak-scaling DDP figure is extras.ddp")
         out["collectives"] = {"backend": p2p.backend(None), "peer_ops": sorted(p2p._OPS) if p2p.backend(None) == "p2p" else [],
                               "note": "p2p = stores / pull-reduces over NVLink peer memory (csrc/a2a.cu) + symmetric-memory barrier; nccl = torch.distributed"}
     extras = {}
