@@ -28,6 +28,7 @@ import torch
 import torch.distributed as dist
 
 _CTX = {}        # id(group) -> _Peer | False
+_MIN_BYTES = {"a2a": 16 << 20, "gather": 64 << 20, "reduce": 64 << 20}
 # which exchanges take the peer path (GAOT_P2P_OPS, comma separated): a2a, ag (all-gather), rs (reduce-scatter), ar (all-reduce)
 _OPS = set(os.environ.get("GAOT_P2P_OPS", "a2a,ag,rs,ar").split(","))
 
@@ -47,8 +48,14 @@ class _Peer:
             return None
         import torch.distributed._symmetric_memory as symm
         g = dist.group.WORLD if self.group is None else self.group
-        size = max(int(nbytes), 1 << 20)
+        # generous first allocation (the step's largest exchange of each kind fits: 44 MB gradient all-reduce, 17 MB latent
+        # field, 13 MB [q|k|v]) so that the pools do not grow in steady state; if one must grow, every rank first drains its GPU
+        # and meets the others: a peer may still be pulling from the buffer that is about to be released
+        size = max(int(nbytes), _MIN_BYTES.get(kind, 1 << 20))
         size = (size + 255) // 256 * 256
+        if p is not None:
+            torch.cuda.synchronize(self.dev)
+            dist.barrier(group=self.group)
         bufs, hdls, ptrs = [], [], []
         for _ in range(2):
             b = symm.empty(size, dtype=torch.uint8, device=self.dev)
