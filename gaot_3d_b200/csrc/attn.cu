@@ -1080,7 +1080,8 @@ constexpr int SMEM = OFF_STG + 4 * 4096;            // 212992 B
 
 // PADK: the sequence has padding keys (S % 128 != 0) -> per-element validity select; EMU: of every 32 exponentials this many
 // run as the FMA-pipe polynomial (ex2_poly)
-// DBG (timing experiments only, results are wrong when non-zero): 1 = no dQ products, 2 = no dS^T shared-memory stores, 4 = no MUFU (multiply instead
+// DBG (timing experiments only, results are wrong when non-zero; NOT instantiated in the library -- profiles/r02e_attn_bwd_ablation.txt was
+// measured with a scratch launcher at commit 1001e31): 1 = no dQ products, 2 = no dS^T shared-memory stores, 4 = no MUFU (multiply instead
 // of ex2), 8 = no dV / dK products, 16 = no dQ drain
 // PREF: the compute warps request the scores of step n+1 from TMEM as soon as the registers of step n are consumed, so the
 // tcgen05.ld latency runs under the store / fence / arrive tail of step n instead of in front of step n+1's exponentials
@@ -1525,37 +1526,23 @@ static int attn_launch_bwd(const AttnWs& w, const float* lse, int64_t B, int64_t
         // measured at S = 16384 (profiles/r02f_attn_variants.txt): 2 stages 1.164 ms; 3 stages 1.188; 2 stages + score prefetch 1.429;
         // 3 stages + score prefetch 1.109 (default).  GAOT_ATTN_BWD_STAGES / GAOT_ATTN_BWD_PREF pick the others for A/B timing.
         static const int bstg = getenv("GAOT_ATTN_BWD_STAGES") ? atoi(getenv("GAOT_ATTN_BWD_STAGES")) : 3;
-        static const int bdbg = getenv("GAOT_ATTN_BWD_DBG") ? atoi(getenv("GAOT_ATTN_BWD_DBG")) : 0;        // ablation timing (wrong results)
         static const int bpref = getenv("GAOT_ATTN_BWD_PREF") ? atoi(getenv("GAOT_ATTN_BWD_PREF")) : (bstg == 3 ? 1 : 0);
 #define GAOT_BWD2_LAUNCH6(NS)                                                                                          \
     do { GAOT_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<16, false, false, 0, NS, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bw2::SMEM)); \
          attn_bwd2_kernel<16, false, false, 0, NS, 0, true><<<grid, (16 + 6) * 32, bw2::SMEM, st>>>(w.Qb, w.Kb, w.Vb, w.dOb, w.Dvec, w.dQacc, w.dKh, w.dVh, \
                                                                                                    (int)S, H, Hkv, scale, scale_dk, dc); } while (0)
-#define GAOT_BWD2_LAUNCH5(DB)                                                                                          \
-    do { GAOT_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<16, false, false, 0, 2, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bw2::SMEM)); \
-         attn_bwd2_kernel<16, false, false, 0, 2, DB><<<grid, (16 + 6) * 32, bw2::SMEM, st>>>(w.Qb, w.Kb, w.Vb, w.dOb, w.Dvec, w.dQacc, w.dKh, w.dVh, \
-                                                                                             (int)S, H, Hkv, scale, scale_dk, dc); } while (0)
 #define GAOT_BWD2_LAUNCH4(PK, EM, NS)                                                                                  \
     do { GAOT_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<16, false, PK, EM, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bw2::SMEM)); \
          attn_bwd2_kernel<16, false, PK, EM, NS><<<grid, (16 + 6) * 32, bw2::SMEM, st>>>(w.Qb, w.Kb, w.Vb, w.dOb, w.Dvec, w.dQacc, w.dKh, w.dVh, \
                                                                                         (int)S, H, Hkv, scale, scale_dk, dc); } while (0)
         if (drop) GAOT_BWD2_LAUNCH(16, true);
         else if (S % 128 != 0) GAOT_BWD2_LAUNCH(16, false);
-        else if (bdbg) {
-            switch (bdbg) {
-                case 1: GAOT_BWD2_LAUNCH5(1); break;   case 2: GAOT_BWD2_LAUNCH5(2); break;   case 3: GAOT_BWD2_LAUNCH5(3); break;
-                case 4: GAOT_BWD2_LAUNCH5(4); break;   case 8: GAOT_BWD2_LAUNCH5(8); break;   case 16: GAOT_BWD2_LAUNCH5(16); break;
-                case 11: GAOT_BWD2_LAUNCH5(11); break; case 27: GAOT_BWD2_LAUNCH5(27); break; case 31: GAOT_BWD2_LAUNCH5(31); break;
-                default: GAOT_BWD2_LAUNCH5(0); break;
-            }
-        }
         else if (bpref) { if (bstg == 3) GAOT_BWD2_LAUNCH6(3); else GAOT_BWD2_LAUNCH6(2); }
         else if (bstg == 3) GAOT_BWD2_LAUNCH4(false, 0, 3);
         else if (bemu >= 8) GAOT_BWD2_LAUNCH4(false, 8, 2);
         else if (bemu >= 4) GAOT_BWD2_LAUNCH4(false, 4, 2);
         else GAOT_BWD2_LAUNCH4(false, 0, 2);
 #undef GAOT_BWD2_LAUNCH6
-#undef GAOT_BWD2_LAUNCH5
 #undef GAOT_BWD2_LAUNCH4
 #undef GAOT_BWD2_LAUNCH
         GAOT_LAUNCH_CHECK();
